@@ -1,0 +1,328 @@
+"""CPU tests of the oracle itself: C restatement vs pure-Python restatement vs standards, and the
+structural facts the reference's own unit tests pin."""
+import hashlib
+import random
+import struct
+
+import numpy as np
+import pytest
+
+GL, BB = 0, 1
+
+
+def rand_elems(field, n, seed, pyref):
+    rng = random.Random(seed)
+    p = pyref.FIELDS[field].p
+    return [rng.randrange(p) for _ in range(n)]
+
+
+# ---- util.rs:46-97 -------------------------------------------------------------------------
+def test_util_values(pyref):
+    R = pyref
+    for v in (0, 1, 2, 32, 128, 512, 1024):
+        assert R.is_power_of_two(v)
+    assert not R.is_power_of_two(24) and not R.is_power_of_two(48)
+    assert R.logarithm_of_two_k(32, 2) == 5 and R.logarithm_of_two_k(256, 4) == 4
+    assert R.logarithm_of_two_k(512, 8) == 3 and R.logarithm_of_two_k(256, 16) == 2
+    for bad in ((6, 2), (12, 4), (32, 4), (15, 8), (16, 8), (48, 16), (64, 16)):
+        with pytest.raises(ValueError):
+            R.logarithm_of_two_k(*bad)
+    assert [R.ceil_log2_k(*a) for a in ((2, 2), (21, 2), (32, 2), (4, 4), (3, 4), (13, 4), (21, 4))] == [1, 5, 5, 2, 2, 4, 6]
+    assert R.ceil_log2_k(1, 2) == 1  # util.rs:33-35
+
+
+# ---- starks.rs:348-374 ----------------------------------------------------------------------
+def test_num_queries(pyref):
+    R = pyref
+    assert R.num_queries_from_config(R.Goldilocks, 20, 4, 129) == (1, 3)
+    assert R.num_queries_from_config(R.Goldilocks, 20, 2, 9) == (1, 10)
+    assert R.num_queries_from_config(R.Goldilocks, 128, 4, 129) == (3, 19)
+    assert R.num_queries_from_config(R.Goldilocks, 256, 4, 513) == (5, 32)
+    with pytest.raises(RuntimeError):
+        R.num_queries_from_config(R.Goldilocks, 1, 4, 128)
+
+
+# ---- field constants (field.rs:43-109, scripts/babybear_arguments.ipynb) ---------------------
+def test_field_constants(pyref, oracle):
+    R = pyref
+    assert R.Goldilocks.root == 1753635133440165772 == oracle.root_of_unity(GL, 32)
+    assert R.BabyBear.root == 291241980 == oracle.root_of_unity(BB, 27)
+    for F in (R.Goldilocks, R.BabyBear):
+        assert pow(F.root, 1 << F.two_adicity, F.p) == 1 and pow(F.root, 1 << (F.two_adicity - 1), F.p) == F.p - 1
+    # Frobenius coefficients quoted in field.rs:57-61, 86-90, 97-106 pin the non-residues
+    p = R.Goldilocks.p
+    assert pow(7, (p - 1) // 2, p) == p - 1
+    q = R.BabyBear.p
+    assert pow(11, (q - 1) // 2, q) == q - 1
+    # field.rs:97-106 (Frobenius coefficients; not used by add/mul) are powers of the Fp2 non-residue 11
+    assert [pow(11, (q**i - 1) // 4, q) for i in range(4)] == [1, 1728404513, 2013265920, 284861408]
+    # v^2 = u - 11 (field.rs:96): check (0,0,1,0)^2 == (q-11, 1, 0, 0)
+    assert R.BabyBear.ext_mul((0, 0, 1, 0), (0, 0, 1, 0)) == (q - 11, 1, 0, 0)
+    assert R.BabyBear.ext_mul((0, 1, 0, 0), (0, 1, 0, 0)) == (11, 0, 0, 0)
+    assert R.Goldilocks.ext_mul((0, 1), (0, 1)) == (7, 0)
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+def test_ext_mul_c_vs_python(field, pyref, oracle):
+    F = pyref.FIELDS[field]
+    rng = random.Random(7)
+    for _ in range(200):
+        a = tuple(rng.randrange(F.p) for _ in range(F.ext_degree))
+        b = tuple(rng.randrange(F.p) for _ in range(F.ext_degree))
+        assert tuple(int(x) for x in oracle.ext_mul(field, a, b)) == F.ext_mul(a, b)
+    # associativity / distributivity sanity of the tower
+    a, b, c = (tuple(rng.randrange(F.p) for _ in range(F.ext_degree)) for _ in range(3))
+    assert F.ext_mul(F.ext_mul(a, b), c) == F.ext_mul(a, F.ext_mul(b, c))
+    assert F.ext_mul(a, F.ext_add(b, c)) == F.ext_add(F.ext_mul(a, b), F.ext_mul(a, c))
+
+
+# ---- SHA-256 / Display / Merkle ---------------------------------------------------------------
+def test_sha256_vs_hashlib(oracle):
+    rng = random.Random(1)
+    for n in [0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 1000]:
+        m = bytes(rng.randrange(256) for _ in range(n))
+        assert oracle.sha256(m) == hashlib.sha256(m).digest()
+    assert oracle.sha256(b"abc").hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+
+
+def test_leaf_string(oracle, pyref):
+    assert oracle.leaf_string([0]) == b"0"
+    assert oracle.leaf_string([18446744069414584320]) == b"18446744069414584320"
+    assert oracle.leaf_string([5, 0], 2) == b"QuadExtField(5 + 0 * u)"
+    assert oracle.leaf_string([1, 2, 3, 4], 4) == b"QuadExtField(QuadExtField(1 + 2 * u) + QuadExtField(3 + 4 * u) * u)"
+    assert pyref.display(pyref.BabyBear, (1, 2, 3, 4)).encode() == oracle.leaf_string([1, 2, 3, 4], 4)
+    oracle.set_zero_display(True)
+    try:
+        assert oracle.leaf_string([0]) == b""
+    finally:
+        oracle.set_zero_display(False)
+
+
+def test_merkle_node_counts_and_shape(oracle, pyref):
+    """merkle.rs:399-419: 16 leaves, (lpn,k) = (2,2),(4,2),(4,4),(16,16) -> 31/23/21/17 nodes incl. leaves."""
+    leaves = list(range(1, 17))
+    for (lpn, k), total in (((2, 2), 31), ((4, 2), 23), ((4, 4), 21), ((16, 16), 17)):
+        t = pyref.MerkleTree(pyref.Goldilocks, leaves, lpn, k)
+        assert t.get_node_number() == total
+        root, nodes = oracle.merkle(leaves, lpn, k, want_nodes=True)
+        assert len(nodes) == total - 16
+        assert [bytes(n) for n in nodes] == t.nodes and root == t.root()
+    with pytest.raises(AssertionError):  # merkle.rs:384-396 non-full tree panics
+        pyref.MerkleTree(pyref.Goldilocks, list(range(12)), 2, 4)
+    with pytest.raises(ValueError):
+        oracle.merkle(list(range(12)), 2, 4)
+
+
+def test_merkle_matches_scripted_leaf_encoding(oracle):
+    """scripts/merkle_tree.py:4-9 hashes sha256(str(value)); lpn=1 leaf groups reproduce it."""
+    vals = [3, 0, 18446744069414584320, 12345678901234567890 % (2**64 - 2**32 + 1)]
+    _, nodes = oracle.merkle(vals, 1, 2, want_nodes=True)
+    for v, n in zip(vals, nodes):
+        assert bytes(n) == hashlib.sha256(str(v).encode()).digest()
+    assert bytes(nodes[4]) == hashlib.sha256(bytes(nodes[0]) + bytes(nodes[1])).digest()
+
+
+def test_merkle_paths_roundtrip(pyref):
+    """merkle.rs:463-481: proof round trip, path lengths 3 (2,2) and 2 (4,2)... on 16 leaves."""
+    F = pyref.Goldilocks
+    leaves = [pow(7, i, F.p) for i in range(16)]
+    for (lpn, k), plen in (((2, 2), 3), ((4, 2), 2), ((4, 4), 1)):
+        t = pyref.MerkleTree(F, leaves, lpn, k)
+        for v in leaves:
+            pr = t.generate_proof(v)
+            assert len(pr.path) == plen and len(pr.leaf_neighbours) == lpn
+            assert pyref.check_proof(F, t.root(), pr)
+        pr.leaf_neighbours[0] ^= 1
+        assert not pyref.check_proof(F, t.root(), pr)
+    with pytest.raises(pyref.MerkleProofError):
+        t.generate_proof(12345)
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+def test_merkle_ext_leaves(field, oracle, pyref):
+    F = pyref.FIELDS[field]
+    rng = random.Random(3)
+    D = F.ext_degree
+    leaves = [tuple(rng.randrange(F.p) if rng.random() < 0.7 else 0 for _ in range(D)) for _ in range(32)]
+    t = pyref.MerkleTree(F, leaves, 2, 2)
+    root, nodes = oracle.merkle(np.array(leaves, dtype=np.uint64), 2, 2, deg=D, want_nodes=True)
+    assert root == t.root() and [bytes(n) for n in nodes] == t.nodes
+
+
+# ---- transforms ----------------------------------------------------------------------------
+@pytest.mark.parametrize("field", [GL, BB])
+def test_ntt_c_vs_python_vs_naive(field, oracle, pyref):
+    F = pyref.FIELDS[field]
+    for n in (1, 2, 8, 64):
+        a = rand_elems(field, n, n, pyref)
+        dom = pyref.Domain.new(F, n)
+        want = pyref.domain_fft(dom, a)
+        assert oracle.ntt(field, a).tolist() == want
+        assert oracle.eval_domain_naive(field, a, n).tolist() == want
+        assert oracle.ntt(field, want, inverse=True).tolist() == a == pyref.domain_ifft(dom, want)
+        # air.rs:306-321: interpolant evaluates back to the trace on domain.element(i)
+        for i in (0, n // 2, n - 1):
+            x = dom.element(i)
+            assert sum(c * pow(x, m, F.p) for m, c in enumerate(a)) % F.p == want[i]
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+@pytest.mark.parametrize("blowup", [2, 4, 8])
+def test_trace_polys_and_lde(field, blowup, oracle, pyref):
+    F = pyref.FIELDS[field]
+    N, W = 32, 3
+    trace = np.array(rand_elems(field, N * W, 11, pyref), dtype=np.uint64).reshape(N, W)
+    polys = oracle.trace_polys(field, trace)
+    dom = pyref.Domain.new(F, N)
+    for c in range(W):
+        assert polys[c].tolist() == pyref.domain_ifft(dom, trace[:, c].tolist())
+    shift = rand_elems(field, 1, 5, pyref)[0]
+    L = blowup * N
+    lde = oracle.coset_lde(field, polys, L, shift)
+    coset = pyref.Domain.new(F, L).get_coset(shift)
+    for c in range(W):
+        want = pyref.domain_fft(coset, polys[c].tolist())
+        assert lde[:, c].tolist() == want
+        assert oracle.eval_domain_naive(field, polys[c], L, shift).tolist() == want
+    assert (oracle.coset_lde(field, polys, L, shift, threads=3) == lde).all()
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+def test_mix_and_openings(field, oracle, pyref):
+    F = pyref.FIELDS[field]
+    N, Cn = 16, 5
+    polys = np.array(rand_elems(field, N * Cn, 2, pyref), dtype=np.uint64).reshape(Cn, N)
+    r = rand_elems(field, 1, 9, pyref)[0]
+    want = [sum(pow(r, i, F.p) * int(polys[i][m]) for i in range(Cn)) % F.p for m in range(N)]
+    assert oracle.mix(field, polys, r).tolist() == want
+    z = tuple(rand_elems(field, F.ext_degree, 4, pyref))
+    got = oracle.eval_base_at_ext(field, polys[0], z)
+    assert tuple(int(x) for x in got) == pyref.poly_eval_ext(F, [F.ext_from_base(int(c)) for c in polys[0]], z)
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+def test_fri_fold_and_quotient(field, oracle, pyref):
+    F = pyref.FIELDS[field]
+    D = F.ext_degree
+    rng = random.Random(21)
+    rx = lambda: tuple(rng.randrange(F.p) for _ in range(D))
+    cfg = pyref.FriConfig(2, 2, 4)
+    for n in (1, 2, 3, 7, 8, 16):
+        poly = [rx() for _ in range(n)]
+        z, alpha = rx(), rx()
+        rnd = pyref.FriRound(F, poly, 2 * max(n, 1), cfg)
+        deep = rnd.get_deep_coeffs(z)
+        folded = rnd.fold_poly(alpha)
+        dv = F.ext_add(deep[0], F.ext_mul(deep[1], alpha))
+        want = pyref._ext_poly_div(F, pyref._ext_poly_sub(F, folded, pyref.trim([dv], pyref._ext_is_zero)), [F.ext_neg(z), F.ext_one()])
+        d, nxt = oracle.fri_fold(field, np.array(poly, dtype=np.uint64), z, alpha)
+        assert [tuple(int(v) for v in x) for x in d] == deep
+        assert [tuple(int(v) for v in x) for x in nxt] == want
+        # exactness: next * (x - z) + deep_value == folded
+        cw = oracle.fri_codeword(field, np.array(poly, dtype=np.uint64), pyref.Domain.new(F, 2 * n).size)
+        assert [tuple(int(v) for v in x) for x in cw] == pyref.ext_domain_fft(pyref.Domain.new(F, cw.shape[0]), poly)
+        # query quotient at a domain point
+        dom = pyref.Domain.new(F, 4 * max(n, 2))
+        x1 = dom.element(3)
+        x2 = F.p - x1
+        y1 = pyref.poly_eval_ext(F, poly, F.ext_from_base(x1))
+        y2 = pyref.poly_eval_ext(F, poly, F.ext_from_base(x2))
+        q = oracle.fri_query_quotient(field, np.array(poly, dtype=np.uint64), x1, x2, y1, y2)
+        assert q.shape[0] == max(n - 2, 0)
+        # q * (x^2 - x1^2) + line == poly at a random point
+        t = rx()
+        qv = pyref.poly_eval_ext(F, [tuple(int(v) for v in x) for x in q], t)
+        dinv = F.inv((x2 - x1) % F.p)
+        a = F.ext_mul_base(F.ext_sub(y2, y1), dinv)
+        b = F.ext_sub(y1, F.ext_mul_base(a, x1))
+        line = F.ext_add(b, F.ext_mul(a, t))
+        van = F.ext_sub(F.ext_mul(t, t), F.ext_from_base(x1 * x1 % F.p))
+        assert F.ext_add(F.ext_mul(qv, van), line) == pyref.poly_eval_ext(F, poly, t)
+
+
+# ---- transcript building blocks -----------------------------------------------------------------
+def test_keccak_permutation_via_sha3(pyref, oracle):
+    def sha3_256(msg):
+        rate = 136
+        st = bytearray(200)
+        m = bytearray(msg) + b"\x06"
+        while len(m) % rate:
+            m += b"\x00"
+        m[-1] |= 0x80
+        for off in range(0, len(m), rate):
+            for i in range(rate):
+                st[i] ^= m[off + i]
+            lanes = list(struct.unpack("<25Q", st))
+            pyref.keccak_f1600(lanes)
+            st = bytearray(struct.pack("<25Q", *lanes))
+        return bytes(st[:32])
+
+    for m in (b"", b"abc", bytes(range(200))):
+        assert sha3_256(m) == hashlib.sha3_256(m).digest()
+    lanes = list(range(25))
+    arr = np.array(lanes, dtype=np.uint64)
+    oracle.lib().or_keccak_f1600(arr.ctypes.data)
+    pyref.keccak_f1600(lanes)
+    assert arr.tolist() == lanes
+
+
+def test_chacha_block_rfc7539(pyref):
+    """ChaCha20 block function test vector (RFC 7539 2.3.2 layout differs in nonce words; here the
+    all-zero key/counter vector of the original ChaCha spec): pins the quarter-round plumbing that
+    the ChaCha12 test_rng restatement reuses."""
+    blk = pyref._chacha_block([0] * 8, 0, 20)
+    raw = struct.pack("<16I", *blk)
+    assert raw[:16].hex() == "76b8e0ada0f13d90405d6ae55386bd28"
+
+
+def test_iopattern_and_transcript_determinism(pyref):
+    R = pyref
+    cfg = R.StarkConfig(R.Goldilocks, 20, 2, 9, 6)
+    assert (cfg.rounds, cfg.constrain_queries, cfg.fri_config.queries) == (5, 1, 10)
+    io = cfg.io.as_bytes()
+    assert io.startswith("\U0001F43A".encode() + b"\0A32commit to original trace\0S24ZK: pick random shift of domain")
+    assert io.endswith(b"\0S80FRI QUERY Phase: choose a random element in the domain")
+    assert cfg.io.ops()[:3] == [("A", 32), ("S", 24), ("A", 32)]
+    assert cfg.io.ops()[3] == ("S", 24 + 48 + 48)  # merged consecutive squeezes
+    t1, t2 = R.Transcript(R.Goldilocks, cfg.io), R.Transcript(R.Goldilocks, cfg.io)
+    t1.add_bytes(bytes(32)); t2.add_bytes(bytes(32))
+    a = t1.challenge_base()
+    assert a == t2.challenge_base() and 0 <= a < R.Goldilocks.p
+    with pytest.raises(R.IOPatternError):
+        t1.challenge_bytes(8)  # pattern expects an absorb next
+    # squeezing in pieces equals squeezing at once (leftover handling)
+    s1, s2 = R.DigestBridge(bytes(32)), R.DigestBridge(bytes(32))
+    s1.absorb(b"x"); s2.absorb(b"x")
+    assert s1.squeeze(100) == s2.squeeze(7) + s2.squeeze(50) + s2.squeeze(43)
+
+
+# ---- end to end: tests/e2e_goldilocks.rs / tests/e2e_babybear.rs ------------------------------------
+@pytest.mark.parametrize("field,steps", [(GL, 9), (BB, 7)])
+def test_e2e_prove_verify(field, steps, pyref):
+    R = pyref
+    F = R.FIELDS[field]
+    claim = R.FibonacciClaim(F, steps)
+    trace = claim.trace(2)
+    # air.rs:251-295 padding dims; :259-266 padding non-zero; constraints vanish on the trace rows
+    assert trace.length == (16 if steps == 9 else 8) and trace.data[-1] != 0
+    cons = trace.derive_constrains()
+    assert len(cons) == 6
+    dom = trace.get_domain()
+    for i in range(trace.step_number() - 1):
+        w = dom.element(i)
+        for idx in (3, 5):  # e2e_goldilocks.rs:84-95 uses constraint polys 2 and 3 times Z_H; here the
+            # transition polys themselves are linear combos of trace polys (SURVEY 3.1 note)
+            assert len(cons.constrains[idx]) <= trace.length
+    cfg = R.StarkConfig(F, 20, 2, trace.step_number(), trace.constrain_number())
+    stark = R.Stark(cfg)
+    proof = stark.prove(claim, 2)
+    assert len(proof.arthur) == 64 + (cfg.rounds - 1) * 64
+    assert stark.verify(cons, proof, strict=True)
+    raw = R.serialize_proof(F, proof)
+    F2, p2 = R.deserialize_proof(raw)
+    assert F2 is F and R.serialize_proof(F, p2) == raw
+    # tampering is caught
+    bad = R.deserialize_proof(raw)[1]
+    bad.validity_queries[0] = F.ext_add(bad.validity_queries[0], F.ext_one())
+    with pytest.raises(AssertionError):
+        stark.verify(cons, bad)
