@@ -1,0 +1,169 @@
+/*
+ * ministark.h -- C ABI of libministark.so, the B200 (sm_100a) implementation of mini-stark's
+ * data-parallel prover core.
+ *
+ * The reference (alv-around/mini-stark, pure Rust) has no FFI: its boundary for this path is the
+ * crate's public API (`StarkConfig::new`, `Stark::prove`, src/starks.rs:59-63,268-273).  Each entry
+ * point below replaces one call site *behind* `Stark::prove`; the `Replaces:` line cites it
+ * (paths relative to the reference root).  INTEGRATION.md shows the Rust `extern "C"` block and
+ * the shim a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns an int32 status (MS_OK = 0); nothing unwinds across the boundary.
+ *    Shape violations the reference turns into panics (src/merkle.rs:95,99-104, src/air.rs:23,
+ *    src/starks.rs:119) come back as MS_ERR_BAD_SHAPE / MS_ERR_QUOTIENT_NONZERO.
+ *  - field elements are canonical integers: uint64_t for Goldilocks, uint32_t for BabyBear.
+ *    Extension elements are D consecutive base elements in ark's tower order (D = 2 / 4).
+ *  - `d_*` arguments are DEVICE pointers (cudaMalloc'ed by the caller, e.g. a torch tensor's
+ *    data_ptr, or ms_dev_alloc); all other pointers are HOST memory owned by the caller.
+ *  - device matrices are column-major ("poly-major"): column c starts at base + c*stride
+ *    elements and holds `rows` contiguous elements.  Extension vectors are D coordinate planes.
+ *  - digests on the device are 8 uint32_t SHA-256 state words; on the host they are the usual 32
+ *    big-endian bytes.
+ *  - a context is bound to one device and one stream and is not thread-safe; calls are
+ *    asynchronous on that stream unless they return host data.
+ */
+#ifndef MINISTARK_H
+#define MINISTARK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    MS_OK = 0,
+    MS_ERR_BAD_SHAPE = 1,        /* reference panics: non-full tree, non power-of-two length ... */
+    MS_ERR_CUDA = 2,
+    MS_ERR_NCCL = 3,
+    MS_ERR_QUOTIENT_NONZERO = 4, /* src/starks.rs:119 assert_eq!(rest, zero) */
+    MS_ERR_TRANSCRIPT = 5,       /* nimue IOPatternError / ProofError (src/error.rs:5-8) */
+    MS_ERR_UNSUPPORTED = 6,
+    MS_ERR_LEAF_NOT_FOUND = 7,   /* src/error.rs:13-16 MerkleProofError::LeafNotFound */
+    MS_ERR_BUFFER_TOO_SMALL = 8
+};
+
+enum { MS_FIELD_GOLDILOCKS = 0, MS_FIELD_BABYBEAR = 1 };
+
+typedef struct ms_ctx ms_ctx;
+
+/* ---- context --------------------------------------------------------------------------- */
+int32_t ms_version(void);
+/* stream: the cudaStream_t to run on (e.g. torch's current stream); NULL = the legacy default stream. */
+int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out);
+void ms_ctx_destroy(ms_ctx* ctx);
+const char* ms_last_error(const ms_ctx* ctx);
+int32_t ms_sync(ms_ctx* ctx);
+/* kernels launched by this library on this context since creation (bench.py gpu_launches) */
+uint64_t ms_launch_count(const ms_ctx* ctx);
+/* Display of the zero element: 0 -> "0" (ark-ff 0.5.0, default), 1 -> "" (ark-ff 0.4.x) */
+int32_t ms_set_zero_display(ms_ctx* ctx, int32_t empty);
+
+int32_t ms_dev_alloc(ms_ctx* ctx, size_t bytes, void** d_out);
+int32_t ms_dev_free(ms_ctx* ctx, void* d_ptr);
+int32_t ms_h2d(ms_ctx* ctx, void* d_dst, const void* src, size_t bytes);
+int32_t ms_d2h(ms_ctx* ctx, void* dst, const void* d_src, size_t bytes);
+
+/* ---- a1: trace layout ------------------------------------------------------------------- */
+/* Row-major N x W trace (the reference's Matrix, src/air.rs:15-59) -> column-major W x N.
+ * Replaces: the stride-W gather of src/air.rs:151-153. */
+int32_t ms_transpose_rm_to_cm(ms_ctx* ctx, const void* d_rowmajor, uint64_t rows, uint64_t width, void* d_colmajor);
+/* Column-major -> row-major (for callers that want the reference's Matrix layout back). */
+int32_t ms_transpose_cm_to_rm(ms_ctx* ctx, const void* d_colmajor, uint64_t rows, uint64_t width, void* d_rowmajor);
+
+/* ---- a1 / a5 / a8: Merkle commitment ------------------------------------------------------ */
+/* MerkleTree::new over the ROW-MAJOR flattening of a column-major device matrix of `rows` x `width`
+ * elements of `deg` coordinates each (deg = 1 base field, deg = D extension planes): leaf group g
+ * hashes SHA256(concat(to_string(e))) of flat elements [g*lpn, (g+1)*lpn), inner nodes hash `k`
+ * child digests, nodes in level order.  d_nodes (optional) receives all (k^levels-1)/(k-1)
+ * digests (8 words each); root32 (optional, host) the root bytes.
+ * Replaces: MerkleTree::new, src/merkle.rs:81-148 with :162-177 (call sites src/starks.rs:70-72,
+ * 92-94, src/fri.rs:351). */
+int32_t ms_merkle_commit(ms_ctx* ctx, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width,
+                         int32_t deg, uint64_t leafs_per_node, uint64_t inner_children,
+                         uint32_t* d_nodes, uint8_t* root32);
+/* number of digests MerkleTree::new produces for n_groups leaf groups (0 if the tree is not full) */
+uint64_t ms_merkle_node_count(uint64_t n_groups, uint64_t inner_children);
+
+/* ---- a2: trace interpolation ---------------------------------------------------------------- */
+/* Per column: coefficients of the degree < N interpolant over the size-N subgroup (iNTT incl. 1/N),
+ * natural order in and out.  Replaces: TraceTable::get_trace_polys, src/air.rs:147-160. */
+int32_t ms_intt_columns(ms_ctx* ctx, const void* d_evals, uint64_t in_stride, uint64_t n, uint64_t cols,
+                        void* d_coeffs, uint64_t out_stride);
+
+/* ---- a3: linear transition constraints -------------------------------------------------------- */
+/* out column t = sum_w M[t*W + w] * coeff column w  (M: host, T x W canonical scalars).  Only
+ * constraints linear in the trace polynomials are provable by the reference.
+ * Replaces: the closures run by TraceTable::derive_constrains, src/air.rs:130-134. */
+int32_t ms_linear_constraints(ms_ctx* ctx, const void* d_coeffs, uint64_t stride, uint64_t n, uint64_t w,
+                              const void* matrix_host, uint64_t t, void* d_out, uint64_t out_stride);
+
+/* ---- a4: coset low-degree extension ----------------------------------------------------------- */
+/* out[c][i] = f_c(shift * w_L^i), L = blowup*n, natural order, for `cols` coefficient columns of
+ * length n.  Replaces: the LDE loop src/starks.rs:82-91 (get_coset + evaluate_over_domain +
+ * Matrix::add_col). */
+int32_t ms_coset_lde(ms_ctx* ctx, const void* d_coeffs, uint64_t in_stride, uint64_t n, uint64_t cols,
+                     uint64_t blowup, uint64_t shift, void* d_out, uint64_t out_stride);
+/* Host-buffer form of the same call (row-major in/out like the reference's Vec<DensePolynomial> ->
+ * Matrix path is NOT assumed: coeffs_host is poly-major [cols][n], out_host is row-major [L][cols]
+ * exactly as src/starks.rs:87-91 leaves `constrain_trace`).  H2D + LDE + D2H; used for `e2e`. */
+int32_t ms_coset_lde_host(ms_ctx* ctx, const void* coeffs_host, uint64_t n, uint64_t cols, uint64_t blowup,
+                          uint64_t shift, void* out_host_rowmajor);
+
+/* ---- a6: constraint mixing ----------------------------------------------------------------------- */
+/* out[m] = sum_i r^i f_i[m].  Replaces: src/starks.rs:108-117. */
+int32_t ms_mix(ms_ctx* ctx, const void* d_coeffs, uint64_t stride, uint64_t n, uint64_t cols, uint64_t r, void* d_out);
+
+/* ---- a7: DEEP-ALI openings ----------------------------------------------------------------------- */
+/* out[q][c] = f_c(z_q) in the extension field (z: host, Q x D; out: host, Q x cols x D).
+ * Replaces: src/starks.rs:140-151 (+ extend_poly src/field.rs:23-32). */
+int32_t ms_deep_open(ms_ctx* ctx, const void* d_coeffs, uint64_t stride, uint64_t n, uint64_t cols,
+                     const void* z_host, uint64_t q, void* out_host);
+
+/* ---- a8-a11: DEEP-FRI ------------------------------------------------------------------------------ */
+/* Codeword of an extension polynomial (D planes of n_coeffs_padded = domain/blowup coefficients,
+ * zero padded) on the size-`domain` subgroup, natural order, plus its (2,2) Merkle tree.
+ * Replaces: FriRound::codeword_commit, src/fri.rs:345-352. */
+int32_t ms_fri_commit(ms_ctx* ctx, const void* d_poly, uint64_t poly_stride, uint64_t domain, uint64_t blowup,
+                      void* d_codeword, uint64_t cw_stride, uint32_t* d_nodes, uint8_t* root32);
+/* d = [f_even(z), f_odd(z)] (host out, 2 x D).  Replaces: get_deep_coeffs, src/fri.rs:354-359. */
+int32_t ms_fri_deep_coeffs(ms_ctx* ctx, const void* d_poly, uint64_t stride, uint64_t n_coeffs, const void* z_host,
+                           void* d_out_host);
+/* next = (f_even + alpha f_odd - (d0 + d1 alpha)) / (x - z), zero padded to n_coeffs/2 entries.
+ * Replaces: src/fri.rs:97-101 with fold_poly :361-372. */
+int32_t ms_fri_fold(ms_ctx* ctx, const void* d_poly, uint64_t stride, uint64_t n_coeffs, const void* z_host,
+                    const void* alpha_host, const void* d_host, void* d_next, uint64_t next_stride);
+
+/* ---- whole prover ------------------------------------------------------------------------------------ */
+typedef struct ms_stark_params {
+    uint64_t security_bits;  /* StarkConfig::new arguments, src/starks.rs:268-273 */
+    uint64_t blowup_factor;
+    uint64_t steps;
+    uint64_t trace_columns;  /* leafs_per_node of the trace / LDE trees (src/starks.rs:297-302) */
+    uint64_t inner_children; /* 2 in the reference (src/starks.rs:299); 4 / 8 = BASELINE configs 3, 5 */
+} ms_stark_params;
+
+/* Parameters StarkConfig::new derives (src/starks.rs:274-277, 312-332). */
+int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* rounds, uint64_t* constrain_queries,
+                        uint64_t* fri_queries);
+
+/* Stark::prove behind the AIR: the caller supplies what `air.trace(&witness)` built -- the row-major
+ * padded N x W trace (src/air.rs:73-96) -- and the transition constraints as a T x W matrix of
+ * canonical scalars (row t: f_{W+t} = sum_w M[t][w] f_w).  The proof comes back in the canonical
+ * dump described in DESIGN.md ("Proof bytes").  If *proof_len is too small the needed size is
+ * written back and MS_ERR_BUFFER_TOO_SMALL returned.
+ * Replaces: Stark::prove, src/starks.rs:59-169 (host transcript: src/fiatshamir.rs:48-64,96-116). */
+int32_t ms_stark_prove(ms_ctx* ctx, const ms_stark_params* p, const void* trace_rowmajor_host, uint64_t n, uint64_t w,
+                       const void* constraint_matrix_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len);
+/* Same with the trace already resident on the device (column-major W x N, stride n). */
+int32_t ms_stark_prove_device(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
+                              const void* constraint_matrix_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len);
+/* per-stage device times (ms) of the last ms_stark_prove* call: fills up to `cap` entries, returns count.
+ * names[i] points to static strings. */
+int32_t ms_stark_last_timings(ms_ctx* ctx, const char** names, float* ms, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+// common.cuh -- context, error plumbing and stream-ordered scratch memory shared by all stages.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/ministark.h"
+
+namespace ms {
+
+struct Ctx {
+    int field = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    std::string err;
+    int zero_display_empty = 0;  // ark-ff 0.4 printed "" for zero; 0.5.0 prints "0" 
+    void* wtab[2] = {nullptr, nullptr};  // plain DIT twiddles, forward / inverse (see ntt.cuh)
+    unsigned long long launches = 0;     // kernels launched by this library (bench gpu_launches)
+    // transcript switches (host prover)
+    uint8_t bridge_masks[3] = {0x00, 0x01, 0x02};
+};
+
+inline int fail(Ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define MS_CUDA(c, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return ms::fail((c), MS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define MS_TRY(expr)                  \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != MS_OK) return rc__; \
+    } while (0)
+
+#define MS_LAUNCH_CHECK(c)                                                                   \
+    do {                                                                                     \
+        (c)->launches++;                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return ms::fail((c), MS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",            \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+// Stream-ordered temporary (cudaMallocAsync pool; release threshold is raised at ctx creation so
+// steady-state allocations never reach the driver).
+struct Scratch {
+    Ctx* c;
+    void* p = nullptr;
+    Scratch(Ctx* ctx) : c(ctx) {}
+    int alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(c, MS_ERR_CUDA, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        return MS_OK;
+    }
+    ~Scratch() {
+        if (p) cudaFreeAsync(p, c->stream);
+    }
+    template <class T>
+    T* as() { return reinterpret_cast<T*>(p); }
+};
+
+inline int ilog2(uint64_t v) {
+    int l = 0;
+    while ((1ULL << l) < v) l++;
+    return l;
+}
+inline bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }
+
+}  // namespace ms

@@ -1,0 +1,228 @@
+// ministark.cu -- C ABI (include/ministark.h) over the sm_100a kernels.  No torch types, no CPU
+// fallback: every entry point either runs the CUDA path or returns an error code.
+#include "common.cuh"
+#include "field.cuh"
+#include "ntt.cuh"
+#include "merkle.cuh"
+#include "poly.cuh"
+#include "fri.cuh"
+#include "prover.cuh"
+
+using namespace ms;
+
+struct ms_ctx : public ms::Ctx {
+    ms::ProverState* prover = nullptr;
+};
+
+#define FIELD_DISPATCH(ctx, CALL)                                            \
+    ((ctx)->field == MS_FIELD_GOLDILOCKS ? CALL(ms::GL) : CALL(ms::BB))
+
+template <class F>
+static int coset_lde_host(Ctx* c, const void* coeffs_host, uint64_t n, uint64_t cols, uint64_t blowup, uint64_t shift,
+                          void* out_rm_host) {
+    using T = typename F::T;
+    const uint64_t L = n * blowup;
+    Scratch din(c), dout(c), drm(c);
+    MS_TRY(din.alloc(n * cols * sizeof(T)));
+    MS_TRY(dout.alloc(L * cols * sizeof(T)));
+    MS_TRY(drm.alloc(L * cols * sizeof(T)));
+    MS_CUDA(c, cudaMemcpyAsync(din.p, coeffs_host, n * cols * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    MS_TRY(lde_batch<F>(c, din.as<T>(), n, cols, ilog2(n), ilog2(blowup), (T)(shift % (uint64_t)F::P), false, dout.as<T>(), L));
+    MS_TRY(transpose<F>(c, dout.as<T>(), drm.as<T>(), L, cols, false));
+    MS_CUDA(c, cudaMemcpyAsync(out_rm_host, drm.p, L * cols * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+extern "C" {
+
+int32_t ms_version(void) { return 1; }
+
+int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out) {
+    if (!out || (field != MS_FIELD_GOLDILOCKS && field != MS_FIELD_BABYBEAR)) return MS_ERR_BAD_SHAPE;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return MS_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return MS_ERR_CUDA;
+    ms_ctx* c = new ms_ctx();
+    c->field = field;
+    c->device = device;
+    // NULL = the legacy default stream (what torch uses unless told otherwise), so that the caller's
+    // copies and this library's kernels are ordered without extra synchronisation
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return MS_OK;
+}
+
+void ms_ctx_destroy(ms_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; i++)
+        if (c->wtab[i]) cudaFree(c->wtab[i]);
+    delete c->prover;
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* ms_last_error(const ms_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int32_t ms_sync(ms_ctx* c) {
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+uint64_t ms_launch_count(const ms_ctx* c) { return c ? c->launches : 0; }
+int32_t ms_set_zero_display(ms_ctx* c, int32_t empty) {
+    c->zero_display_empty = empty ? 1 : 0;
+    return MS_OK;
+}
+
+int32_t ms_dev_alloc(ms_ctx* c, size_t bytes, void** d_out) {
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaMalloc(d_out, bytes ? bytes : 16));
+    return MS_OK;
+}
+int32_t ms_dev_free(ms_ctx* c, void* p) {
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    MS_CUDA(c, cudaFree(p));
+    return MS_OK;
+}
+int32_t ms_h2d(ms_ctx* c, void* d, const void* s, size_t bytes) {
+    MS_CUDA(c, cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+int32_t ms_d2h(ms_ctx* c, void* d, const void* s, size_t bytes) {
+    MS_CUDA(c, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+int32_t ms_transpose_rm_to_cm(ms_ctx* c, const void* d_rm, uint64_t rows, uint64_t width, void* d_cm) {
+#define CALL(F) transpose<F>(c, (const F::T*)d_rm, (F::T*)d_cm, rows, width, true)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+int32_t ms_transpose_cm_to_rm(ms_ctx* c, const void* d_cm, uint64_t rows, uint64_t width, void* d_rm) {
+#define CALL(F) transpose<F>(c, (const F::T*)d_cm, (F::T*)d_rm, rows, width, false)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+uint64_t ms_merkle_node_count(uint64_t n_groups, uint64_t k) { return merkle_node_count(n_groups, k); }
+
+int32_t ms_merkle_commit(ms_ctx* c, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width, int32_t deg,
+                         uint64_t lpn, uint64_t k, uint32_t* d_nodes, uint8_t* root32) {
+#define CALL(F) merkle_commit<F>(c, (const F::T*)d_data, stride, rows, width, deg, lpn, k, d_nodes, root32)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_intt_columns(ms_ctx* c, const void* d_evals, uint64_t in_stride, uint64_t n, uint64_t cols, void* d_coeffs,
+                        uint64_t out_stride) {
+    if (!is_pow2(n)) return fail(c, MS_ERR_BAD_SHAPE, "trace length %llu is not a power of two (air.rs:23)", (unsigned long long)n);
+#define CALL(F) lde_batch<F>(c, (const F::T*)d_evals, in_stride, cols, ilog2(n), 0, (F::T)1, true, (F::T*)d_coeffs, out_stride)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_coset_lde(ms_ctx* c, const void* d_coeffs, uint64_t in_stride, uint64_t n, uint64_t cols, uint64_t blowup,
+                     uint64_t shift, void* d_out, uint64_t out_stride) {
+    if (!is_pow2(n) || !is_pow2(blowup)) return fail(c, MS_ERR_BAD_SHAPE, "n and blowup must be powers of two");
+#define CALL(F)                                                                                             \
+    ((shift % (uint64_t)F::P) == 0 ? fail(c, MS_ERR_BAD_SHAPE, "coset offset is zero (starks.rs:84 unwrap)") \
+                                   : lde_batch<F>(c, (const F::T*)d_coeffs, in_stride, cols, ilog2(n), ilog2(blowup), \
+                                                  (F::T)(shift % (uint64_t)F::P), false, (F::T*)d_out, out_stride))
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_coset_lde_host(ms_ctx* c, const void* coeffs_host, uint64_t n, uint64_t cols, uint64_t blowup, uint64_t shift,
+                          void* out_host_rowmajor) {
+    if (!is_pow2(n) || !is_pow2(blowup)) return fail(c, MS_ERR_BAD_SHAPE, "n and blowup must be powers of two");
+#define CALL(F) coset_lde_host<F>(c, coeffs_host, n, cols, blowup, shift, out_host_rowmajor)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_linear_constraints(ms_ctx* c, const void* d_coeffs, uint64_t stride, uint64_t n, uint64_t w, const void* matrix_host,
+                              uint64_t t, void* d_out, uint64_t out_stride) {
+#define CALL(F) linear_constraints<F>(c, (const F::T*)d_coeffs, stride, n, w, (const F::T*)matrix_host, t, (F::T*)d_out, out_stride)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_mix(ms_ctx* c, const void* d_coeffs, uint64_t stride, uint64_t n, uint64_t cols, uint64_t r, void* d_out) {
+#define CALL(F) mix<F>(c, (const F::T*)d_coeffs, stride, n, cols, (F::T)(r % (uint64_t)F::P), (F::T*)d_out)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_deep_open(ms_ctx* c, const void* d_coeffs, uint64_t stride, uint64_t n, uint64_t cols, const void* z_host, uint64_t q,
+                     void* out_host) {
+#define CALL(F) deep_open<F>(c, (const F::T*)d_coeffs, stride, n, cols, (const F::T*)z_host, q, (F::T*)out_host)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_fri_commit(ms_ctx* c, const void* d_poly, uint64_t poly_stride, uint64_t domain, uint64_t blowup, void* d_codeword,
+                      uint64_t cw_stride, uint32_t* d_nodes, uint8_t* root32) {
+#define CALL(F) fri_commit<F>(c, (const F::T*)d_poly, poly_stride, domain, blowup, (F::T*)d_codeword, cw_stride, d_nodes, root32)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_fri_deep_coeffs(ms_ctx* c, const void* d_poly, uint64_t stride, uint64_t n_coeffs, const void* z_host, void* d_out_host) {
+#define CALL(F) fri_deep_coeffs<F>(c, (const F::T*)d_poly, stride, n_coeffs, (const F::T*)z_host, (F::T*)d_out_host)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_fri_fold(ms_ctx* c, const void* d_poly, uint64_t stride, uint64_t n_coeffs, const void* z_host, const void* alpha_host,
+                    const void* d_host, void* d_next, uint64_t next_stride) {
+#define CALL(F) fri_fold<F>(c, (const F::T*)d_poly, stride, n_coeffs, (const F::T*)z_host, (const F::T*)alpha_host, (const F::T*)d_host, (F::T*)d_next, next_stride)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* rounds, uint64_t* cq, uint64_t* fq) {
+    ms::StarkDerived d;
+    int rc = ms::stark_derive(field, *p, &d);
+    if (rc != MS_OK) return rc;
+    if (rounds) *rounds = d.rounds;
+    if (cq) *cq = d.constrain_queries;
+    if (fq) *fq = d.fri_queries;
+    return MS_OK;
+}
+
+int32_t ms_stark_prove(ms_ctx* c, const ms_stark_params* p, const void* trace_rm_host, uint64_t n, uint64_t w,
+                       const void* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
+    if (!c->prover) c->prover = new ms::ProverState();
+#define CALL(F) stark_prove<F>(c, c->prover, *p, trace_rm_host, nullptr, n, w, (const F::T*)cmat_host, t, proof_out, proof_len)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+int32_t ms_stark_prove_device(ms_ctx* c, const ms_stark_params* p, const void* d_trace_cm, uint64_t n, uint64_t w,
+                              const void* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
+    if (!c->prover) c->prover = new ms::ProverState();
+#define CALL(F) stark_prove<F>(c, c->prover, *p, nullptr, d_trace_cm, n, w, (const F::T*)cmat_host, t, proof_out, proof_len)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+int32_t ms_stark_last_timings(ms_ctx* c, const char** names, float* msv, int32_t cap) {
+    if (!c->prover) return 0;
+    int n = 0;
+    for (auto& e : c->prover->timings) {
+        if (n >= cap) break;
+        names[n] = e.first;
+        msv[n] = e.second;
+        n++;
+    }
+    return n;
+}
+
+}  // extern "C"
