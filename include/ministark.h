@@ -148,6 +148,9 @@ typedef struct ms_stark_params {
 int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* rounds, uint64_t* constrain_queries,
                         uint64_t* fri_queries);
 
+/* Upper bound (bytes) of the proof dump for an n x (cols = W + T) problem; 0 on bad parameters. */
+uint64_t ms_stark_proof_bound(int32_t field, const ms_stark_params* p, uint64_t n, uint64_t cols);
+
 /* Stark::prove behind the AIR: the caller supplies what `air.trace(&witness)` built -- the row-major
  * padded N x W trace (src/air.rs:73-96) -- and the transition constraints as a T x W matrix of
  * canonical scalars (row t: f_{W+t} = sum_w M[t][w] f_w).  The proof comes back in the canonical

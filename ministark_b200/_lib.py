@@ -53,6 +53,7 @@ SIGNATURES = {
     "ms_fri_deep_coeffs": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "ms_fri_fold": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64]),
     "ms_stark_derive": (_i32, [_i32, C.POINTER(StarkParams), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "ms_stark_proof_bound": (_u64, [_i32, C.POINTER(StarkParams), _u64, _u64]),
     "ms_stark_prove": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_device": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_last_timings": (_i32, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i32]),

@@ -64,6 +64,9 @@ struct Scratch {
     Ctx* c;
     void* p = nullptr;
     Scratch(Ctx* ctx) : c(ctx) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    Scratch(Scratch&& o) noexcept : c(o.c), p(o.p) { o.p = nullptr; }
     int alloc(size_t bytes) {
         if (bytes == 0) bytes = 16;
         cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);

@@ -1,8 +1,178 @@
+// fri.cuh -- DEEP-FRI stages (src/fri.rs).  Extension polynomials / codewords live on the device
+// as D coordinate planes of base-field elements, zero padded to a power of two.
+//   a8   codeword + (2,2) Merkle tree per round       src/fri.rs:314-352
+//   a9   d = [f_even(z), f_odd(z)]                      src/fri.rs:354-359
+//   a10  next = (f_even + alpha f_odd - d(alpha)) / (x - z)   src/fri.rs:97-101, 361-372
+//   (f)  query phase: openings by value search, per-query quotients   src/fri.rs:132-172
 #pragma once
 #include "common.cuh"
 #include "field.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+#include "poly.cuh"
+
 namespace ms {
-template <class F> int fri_commit(Ctx* c, const typename F::T*, uint64_t, uint64_t, uint64_t, typename F::T*, uint64_t, uint32_t*, uint8_t*) { return fail(c, MS_ERR_UNSUPPORTED, "not built yet"); }
-template <class F> int fri_deep_coeffs(Ctx* c, const typename F::T*, uint64_t, uint64_t, const typename F::T*, typename F::T*) { return fail(c, MS_ERR_UNSUPPORTED, "not built yet"); }
-template <class F> int fri_fold(Ctx* c, const typename F::T*, uint64_t, uint64_t, const typename F::T*, const typename F::T*, const typename F::T*, typename F::T*, uint64_t) { return fail(c, MS_ERR_UNSUPPORTED, "not built yet"); }
+
+// a8.  ark embeds the base-field root into the extension, so the extension FFT is
+// D independent base-field transforms: the poly's D planes go through lde_batch as D columns with
+// shift 1 (plain subgroup, fri.rs:315), then leaves are pairs of adjacent evaluations (fri.rs:351
+// with leafs_per_node = 2, starks.rs:290-295).
+template <class F>
+int fri_commit(Ctx* c, const typename F::T* d_poly, uint64_t poly_stride, uint64_t domain, uint64_t blowup,
+               typename F::T* d_cw, uint64_t cw_stride, uint32_t* d_nodes, uint8_t* root32) {
+    if (!is_pow2(domain) || !is_pow2(blowup) || domain < blowup || domain < 2)
+        return fail(c, MS_ERR_BAD_SHAPE, "FRI domain %llu / blowup %llu", (unsigned long long)domain, (unsigned long long)blowup);
+    const uint64_t npad = domain / blowup;
+    MS_TRY(lde_batch<F>(c, d_poly, poly_stride, F::D, ilog2(npad), ilog2(blowup), (typename F::T)1, false, d_cw, cw_stride));
+    return merkle_commit<F>(c, d_cw, cw_stride, domain, 1, F::D, 2, 2, d_nodes, root32);
 }
+
+template <class F>
+inline Ext<F> ext_from_host(const typename F::T* p) {
+    Ext<F> r;
+    for (int d = 0; d < F::D; d++) r.c[d] = (typename F::T)((uint64_t)p[d] % (uint64_t)F::P);
+    return r;
+}
+
+// a9.  split_poly (fri.rs:329-343) is the even / odd coefficient subsequence: off = parity, step = 2.
+template <class F>
+int fri_deep_coeffs(Ctx* c, const typename F::T* d_poly, uint64_t stride, uint64_t n, const typename F::T* z_host,
+                    typename F::T* d_out_host) {
+    Ext<F> z = ext_from_host<F>(z_host);
+    Ext<F>* out = reinterpret_cast<Ext<F>*>(d_out_host);
+    MS_TRY(eval_points<F>(c, d_poly, stride, 0, 2, (n + 1) / 2, F::D, 1, &z, 1, &out[0]));
+    MS_TRY(eval_points<F>(c, d_poly, stride, 1, 2, n / 2, F::D, 1, &z, 1, &out[1]));
+    return MS_OK;
+}
+
+// a10.  element i of the folded, DEEP-adjusted sequence
+template <class F>
+struct FoldSrc {
+    const typename F::T* p;
+    uint64_t stride, n;
+    Ext<F> alpha, deep_value;
+    __device__ __forceinline__ Ext<F> operator()(uint32_t, uint64_t i) const {
+        Ext<F> e = ext_zero<F>(), o = ext_zero<F>();
+        const uint64_t i0 = 2 * i, i1 = 2 * i + 1;
+#pragma unroll
+        for (int d = 0; d < F::D; d++) {
+            if (i0 < n) e.c[d] = p[(uint64_t)d * stride + i0];
+            if (i1 < n) o.c[d] = p[(uint64_t)d * stride + i1];
+        }
+        Ext<F> f = ext_add(e, ext_mul(alpha, o));
+        if (i == 0) f = ext_sub(f, deep_value);
+        return f;
+    }
+};
+template <class F>
+struct PlanesDst {
+    typename F::T* p;
+    uint64_t stride;
+    __device__ __forceinline__ void operator()(uint32_t, uint64_t i, const Ext<F>& v) const {
+#pragma unroll
+        for (int d = 0; d < F::D; d++) p[(uint64_t)d * stride + i] = v.c[d];
+    }
+};
+
+// next[k] = q_k for k < ceil(n/2) (q_{last} = 0 keeps the zero padding), planes of stride next_stride
+template <class F>
+int fri_fold(Ctx* c, const typename F::T* d_poly, uint64_t stride, uint64_t n, const typename F::T* z_host,
+             const typename F::T* alpha_host, const typename F::T* d_host, typename F::T* d_next, uint64_t next_stride) {
+    Ext<F> z = ext_from_host<F>(z_host), alpha = ext_from_host<F>(alpha_host);
+    Ext<F> d0 = ext_from_host<F>(d_host), d1 = ext_from_host<F>(d_host + F::D);
+    FoldSrc<F> src{d_poly, stride, n, alpha, ext_add(d0, ext_mul(d1, alpha))};
+    const uint64_t len = (n + 1) / 2;
+    if (len == 0) return MS_OK;
+    return suffix_scan<ExtOps<F>, FoldSrc<F>, PlanesDst<F>>(c, src, len, 1, &z, PlanesDst<F>{d_next, next_stride});
+}
+
+// ------------------------------------------------------------------------------------------ query phase
+// Quotient by (x - x1)(x - x2) = x^2 - s, s = x1^2 (x2 = -x1, fri.rs:149).  q_k only involves
+// coefficients of index >= k + 2, so the linear interpolant a x + b (fri.rs:159-161) never enters a
+// quotient coefficient (it only cancels the remainder): q_k = T(k+2) with T(j) = c_j + s T(j+2),
+// an independent base-field scan per coordinate plane and parity.  Output is AoS (D coordinates
+// per coefficient), i.e. already the little-endian byte layout of the proof dump.
+// batch b = (query k, plane d, parity par): b = (k*D + d)*2 + par; all queries read the same polynomial
+template <class F>
+struct ParitySrc {
+    const typename F::T* p;
+    uint64_t stride, len;
+    __device__ __forceinline__ typename F::T operator()(uint32_t b, uint64_t i) const {
+        uint32_t par = b & 1u, d = (b >> 1) % F::D;
+        uint64_t j = 2 * i + par;
+        return j < len ? p[(uint64_t)d * stride + j] : (typename F::T)0;
+    }
+};
+template <class F>
+struct QuotDst {
+    typename F::T* out;  // [query][nq][D] AoS
+    uint64_t nq;
+    // sequence position i <-> coefficient index j = 2i + parity; the scan's value T(j + 2) is q_j
+    __device__ __forceinline__ void operator()(uint32_t b, uint64_t i, typename F::T v) const {
+        uint32_t par = b & 1u, d = (b >> 1) % F::D, k = (b >> 1) / F::D;
+        uint64_t j = 2 * i + par;
+        if (j < nq) out[((uint64_t)k * nq + j) * F::D + d] = v;
+    }
+};
+
+// quotients of one FRI round for `nq_queries` queries; s_host[k] = x1_k^2; out: [queries][len-2][D]
+template <class F>
+int fri_query_quotients(Ctx* c, const typename F::T* d_poly, uint64_t stride, uint64_t len, const typename F::T* s_host,
+                        uint32_t queries, typename F::T* d_out_aos) {
+    if (len < 3 || queries == 0) return MS_OK;
+    const uint64_t nq = len - 2;
+    std::vector<typename F::T> mus((size_t)queries * F::D * 2);
+    for (uint32_t k = 0; k < queries; k++)
+        for (int i = 0; i < F::D * 2; i++) mus[(size_t)k * F::D * 2 + i] = s_host[k];
+    return suffix_scan<BaseOps<F>, ParitySrc<F>, QuotDst<F>>(c, ParitySrc<F>{d_poly, stride, len}, (len + 1) / 2, queries * F::D * 2,
+                                                             mus.data(), QuotDst<F>{d_out_aos, nq});
+}
+
+// first index (natural order) whose extension value equals each target (merkle.rs:216-225)
+template <class F>
+__global__ void k_find_first(const typename F::T* __restrict__ cw, uint64_t stride, uint64_t n, const Ext<F>* __restrict__ targets,
+                             int nt, unsigned long long* __restrict__ found) {
+    extern __shared__ unsigned char sm_raw[];
+    Ext<F>* tg = reinterpret_cast<Ext<F>*>(sm_raw);
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) tg[i] = targets[i];
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ext<F> v;
+#pragma unroll
+    for (int d = 0; d < F::D; d++) v.c[d] = cw[(uint64_t)d * stride + i];
+    for (int k = 0; k < nt; k++)
+        if (ext_eq(v, tg[k]) && (unsigned long long)i < found[k]) atomicMin(&found[k], (unsigned long long)i);
+}
+
+// gather: values[k] = codeword[idx[k]] (AoS), for the y1/y2/y3 look-ups and leaf neighbours
+template <class F>
+__global__ void k_gather_ext(const typename F::T* __restrict__ cw, uint64_t stride, const unsigned long long* __restrict__ idx, int n,
+                             Ext<F>* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Ext<F> v;
+#pragma unroll
+    for (int d = 0; d < F::D; d++) v.c[d] = cw[(uint64_t)d * stride + idx[k]];
+    out[k] = v;
+}
+
+// authentication path of a binary (2,2) tree: for level l = 0.. the sibling PAIR containing node
+// (leaf_idx/2) >> l of that level (merkle.rs:241-265).  out: [nt][levels-1][2][8] words.
+__global__ void k_gather_paths(const uint32_t* __restrict__ nodes, uint64_t n_groups, int path_len,
+                               const unsigned long long* __restrict__ leaf_idx, int nt, uint32_t* __restrict__ out) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int per = path_len * 16;
+    if (tid >= nt * per) return;
+    int k = tid / per, rem = tid % per, l = rem / 16, w = rem % 16;
+    uint64_t node = (uint64_t)(leaf_idx[k] >> 1) >> l;
+    uint64_t off = 0, lv = n_groups;
+    for (int i = 0; i < l; i++) {
+        off += lv;
+        lv >>= 1;
+    }
+    uint64_t pair = node & ~1ULL;
+    out[tid] = nodes[(off + pair) * 8 + w];
+}
+
+}  // namespace ms

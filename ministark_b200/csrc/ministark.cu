@@ -199,6 +199,12 @@ int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* round
     return MS_OK;
 }
 
+uint64_t ms_stark_proof_bound(int32_t field, const ms_stark_params* p, uint64_t n, uint64_t cols) {
+    ms::StarkDerived d;
+    if (ms::stark_derive(field, *p, &d) != MS_OK) return 0;
+    return field == MS_FIELD_GOLDILOCKS ? ms::proof_size_bound<ms::GL>(*p, d, n, cols) : ms::proof_size_bound<ms::BB>(*p, d, n, cols);
+}
+
 int32_t ms_stark_prove(ms_ctx* c, const ms_stark_params* p, const void* trace_rm_host, uint64_t n, uint64_t w,
                        const void* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
     if (!c->prover) c->prover = new ms::ProverState();

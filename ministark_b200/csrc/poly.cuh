@@ -226,27 +226,30 @@ __device__ __forceinline__ typename Ops::M mpow(typename Ops::M b, uint64_t e) {
 
 constexpr int SC_THREADS = 256;
 
-// One block handles SC_THREADS*seg consecutive elements.
+// One block handles SC_THREADS*seg consecutive elements of batch blockIdx.y (multiplier mus[batch]).
 //   blocksum != nullptr : write H_b = sum_{i in block} e_i mu^(i - start_b)         (phase A)
 //   otherwise           : tails[b] (or zero) is T(end_b); write dst(i) = T(i+1)       (phase B)
+// Elements past a batch's own length must read as zero (Src's job); Dst drops what it does not want.
 template <class Ops, class Src, class Dst>
 __global__ void __launch_bounds__(SC_THREADS)
-k_suffix_scan(Src src, uint64_t len, typename Ops::M mu, uint32_t seg, const typename Ops::V* __restrict__ tails,
-              Dst dst, typename Ops::V* __restrict__ blocksum) {
+k_suffix_scan(Src src, uint64_t len, const typename Ops::M* __restrict__ mus, uint32_t seg,
+              const typename Ops::V* __restrict__ tails, Dst dst, typename Ops::V* __restrict__ blocksum) {
     using V = typename Ops::V;
     using M = typename Ops::M;
     __shared__ V sm[SC_THREADS + 1];
     const int t = threadIdx.x;
+    const uint32_t batch = blockIdx.y;
+    const M mu = mus[batch];
     const uint64_t start = ((uint64_t)blockIdx.x * SC_THREADS + t) * seg;
     // local Horner value of this thread's segment
     V h = Ops::zero();
     for (uint32_t k = seg; k-- > 0;) {
         uint64_t i = start + k;
-        V e = i < len ? src(i) : Ops::zero();
+        V e = i < len ? src(batch, i) : Ops::zero();
         h = Ops::add(Ops::mulm(h, mu), e);
     }
     sm[t] = h;
-    if (t == 0) sm[SC_THREADS] = (!blocksum && tails) ? tails[blockIdx.x] : Ops::zero();
+    if (t == 0) sm[SC_THREADS] = (!blocksum && tails) ? tails[(uint64_t)batch * gridDim.x + blockIdx.x] : Ops::zero();
     // inclusive suffix scan over SC_THREADS + 1 items, all with span mu^seg
     M pw = mpow<Ops>(mu, seg);
     for (int ofs = 1; ofs <= SC_THREADS; ofs <<= 1) {
@@ -260,71 +263,74 @@ k_suffix_scan(Src src, uint64_t len, typename Ops::M mu, uint32_t seg, const typ
     }
     __syncthreads();
     if (blocksum) {
-        if (t == 0) blocksum[blockIdx.x] = sm[0];
+        if (t == 0) blocksum[(uint64_t)batch * gridDim.x + blockIdx.x] = sm[0];
         return;
     }
     V r = sm[t + 1];  // T(end of this thread's segment)
     for (uint32_t k = seg; k-- > 0;) {
         uint64_t i = start + k;
         if (i < len) {
-            dst(i, r);
-            r = Ops::add(src(i), Ops::mulm(r, mu));
+            dst(batch, i, r);
+            r = Ops::add(src(batch, i), Ops::mulm(r, mu));
         }
     }
 }
 
 template <class V>
-struct ArraySrc {
+struct ArraySrc {  // [batch][n]
     const V* p;
-    __device__ __forceinline__ V operator()(uint64_t i) const { return p[i]; }
+    uint64_t n;
+    __device__ __forceinline__ V operator()(uint32_t b, uint64_t i) const { return p[(uint64_t)b * n + i]; }
 };
 template <class V>
 struct ArrayDst {
     V* p;
-    __device__ __forceinline__ void operator()(uint64_t i, const V& v) const { p[i] = v; }
+    uint64_t n;
+    __device__ __forceinline__ void operator()(uint32_t b, uint64_t i, const V& v) const { p[(uint64_t)b * n + i] = v; }
 };
 template <class V>
 struct NullDst {
-    __device__ __forceinline__ void operator()(uint64_t, const V&) const {}
+    __device__ __forceinline__ void operator()(uint32_t, uint64_t, const V&) const {}
 };
 
+// `nbatch` independent scans of (padded) length len; mus_host[b] is batch b's multiplier.
 template <class Ops, class Src, class Dst>
-int suffix_scan(Ctx* c, Src src, uint64_t len, typename Ops::M mu, Dst dst) {
+int suffix_scan(Ctx* c, Src src, uint64_t len, uint32_t nbatch, const typename Ops::M* mus_host, Dst dst) {
     using V = typename Ops::V;
-    if (len == 0) return MS_OK;
+    using M = typename Ops::M;
+    if (len == 0 || nbatch == 0) return MS_OK;
     const uint32_t seg = 8;
-    const uint64_t per_block = (uint64_t)SC_THREADS * seg;
+    const uint64_t per_block = (uint64_t)SC_THREADS * seg;  // a power of two
     const uint64_t nblk = (len + per_block - 1) / per_block;
+    if (nblk > (uint64_t)SC_THREADS * 4096) return fail(c, MS_ERR_UNSUPPORTED, "suffix scan too long");
+    std::vector<M> hm(2 * (size_t)nbatch);
+    for (uint32_t b = 0; b < nbatch; b++) {
+        M r = mus_host[b];
+        hm[b] = r;
+        for (uint64_t e = per_block; e > 1; e >>= 1) r = Ops::mm(r, r);  // mu^per_block
+        hm[nbatch + b] = r;
+    }
+    Scratch dmu(c);
+    MS_TRY(dmu.alloc(hm.size() * sizeof(M)));
+    MS_CUDA(c, cudaMemcpyAsync(dmu.p, hm.data(), hm.size() * sizeof(M), cudaMemcpyHostToDevice, c->stream));
+    const M* d_mu = dmu.as<M>();
+    const M* d_big = d_mu + nbatch;
     if (nblk == 1) {
-        k_suffix_scan<Ops, Src, Dst><<<1, SC_THREADS, 0, c->stream>>>(src, len, mu, seg, nullptr, dst, nullptr);
+        k_suffix_scan<Ops, Src, Dst><<<dim3(1, nbatch), SC_THREADS, 0, c->stream>>>(src, len, d_mu, seg, nullptr, dst, nullptr);
         MS_LAUNCH_CHECK(c);
         return MS_OK;
     }
-    if (nblk > (uint64_t)SC_THREADS * 4096) return fail(c, MS_ERR_UNSUPPORTED, "suffix scan too long");
     Scratch sums(c), tails(c);
-    MS_TRY(sums.alloc(nblk * sizeof(V)));
-    MS_TRY(tails.alloc(nblk * sizeof(V)));
-    k_suffix_scan<Ops, Src, NullDst<V>><<<(unsigned)nblk, SC_THREADS, 0, c->stream>>>(src, len, mu, seg, nullptr, NullDst<V>{}, sums.as<V>());
+    MS_TRY(sums.alloc(nblk * nbatch * sizeof(V)));
+    MS_TRY(tails.alloc(nblk * nbatch * sizeof(V)));
+    k_suffix_scan<Ops, Src, NullDst<V>><<<dim3((unsigned)nblk, nbatch), SC_THREADS, 0, c->stream>>>(src, len, d_mu, seg, nullptr, NullDst<V>{}, sums.as<V>());
     MS_LAUNCH_CHECK(c);
-    // tails[b] = T(end_b) = sum_{b' > b} H_b' * (mu^per_block)^(b'-b-1): the same scan over the block sums
-    typename Ops::M big = mu;
-    {
-        // mu^per_block on the host would need host field ops for both Ops flavours; do it on device
-        // through the kernel's own mpow by passing seg2 and the base multiplier: the block-sum
-        // sequence is scanned with multiplier mu^per_block, computed here by repeated squaring.
-        uint64_t e = per_block;
-        typename Ops::M r = mu;  // per_block is a power of two: square log2(per_block) times
-        while (e > 1) {
-            r = Ops::mm(r, r);
-            e >>= 1;
-        }
-        big = r;
-    }
+    // tails[b] = T(end_b): the same scan over the block sums with multiplier mu^per_block
     const uint32_t seg2 = (uint32_t)((nblk + SC_THREADS - 1) / SC_THREADS);
-    k_suffix_scan<Ops, ArraySrc<V>, ArrayDst<V>><<<1, SC_THREADS, 0, c->stream>>>(ArraySrc<V>{sums.as<V>()}, nblk, big, seg2, nullptr,
-                                                                                 ArrayDst<V>{tails.as<V>()}, nullptr);
+    k_suffix_scan<Ops, ArraySrc<V>, ArrayDst<V>><<<dim3(1, nbatch), SC_THREADS, 0, c->stream>>>(
+        ArraySrc<V>{sums.as<V>(), nblk}, nblk, d_big, seg2, nullptr, ArrayDst<V>{tails.as<V>(), nblk}, nullptr);
     MS_LAUNCH_CHECK(c);
-    k_suffix_scan<Ops, Src, Dst><<<(unsigned)nblk, SC_THREADS, 0, c->stream>>>(src, len, mu, seg, tails.as<V>(), dst, nullptr);
+    k_suffix_scan<Ops, Src, Dst><<<dim3((unsigned)nblk, nbatch), SC_THREADS, 0, c->stream>>>(src, len, d_mu, seg, tails.as<V>(), dst, nullptr);
     MS_LAUNCH_CHECK(c);
     return MS_OK;
 }

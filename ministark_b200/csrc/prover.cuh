@@ -1,10 +1,392 @@
+// prover.cuh -- Stark::prove behind the AIR (src/starks.rs:59-169) and Fri::prove (src/fri.rs:53-189):
+// the host walks the reference's sequence of transcript operations; between two transcript steps
+// all bulk data stays on the device.  What crosses the PCIe bus per step is a 32-byte root, a few
+// field elements, and at the very end the proof (whose size is dominated by the per-query FRI
+// quotient polynomials the reference puts in it, fri.rs:167).
 #pragma once
 #include <utility>
+
 #include "common.cuh"
 #include "field.cuh"
+#include "fri.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+#include "poly.cuh"
+#include "transcript.hpp"
+
 namespace ms {
-struct StarkDerived { uint64_t rounds, constrain_queries, fri_queries; };
-struct ProverState { std::vector<std::pair<const char*, float>> timings; };
-inline int stark_derive(int, const ms_stark_params&, StarkDerived*) { return MS_ERR_UNSUPPORTED; }
-template <class F> int stark_prove(Ctx* c, ProverState*, const ms_stark_params&, const void*, const void*, uint64_t, uint64_t, const typename F::T*, uint64_t, uint8_t*, uint64_t*) { return fail(c, MS_ERR_UNSUPPORTED, "not built yet"); }
+
+struct ProverState {
+    std::vector<std::pair<const char*, float>> timings;
+};
+
+struct StageTimer {
+    Ctx* c;
+    ProverState* ps;
+    cudaEvent_t ev[2];
+    const char* name = nullptr;
+    StageTimer(Ctx* ctx, ProverState* p) : c(ctx), ps(p) {
+        cudaEventCreate(&ev[0]);
+        cudaEventCreate(&ev[1]);
+    }
+    ~StageTimer() {
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    }
+    void begin(const char* n) {
+        name = n;
+        cudaEventRecord(ev[0], c->stream);
+    }
+    void end() {
+        cudaEventRecord(ev[1], c->stream);
+        cudaEventSynchronize(ev[1]);
+        float ms_ = 0;
+        cudaEventElapsedTime(&ms_, ev[0], ev[1]);
+        for (auto& e : ps->timings)
+            if (e.first == name) {
+                e.second += ms_;
+                return;
+            }
+        ps->timings.emplace_back(name, ms_);
+    }
+};
+
+struct ProofWriter {
+    uint8_t* out;
+    uint64_t cap, pos = 0;
+    ProofWriter(uint8_t* o, uint64_t c) : out(o), cap(c) {}
+    void bytes(const void* p, size_t n) {
+        if (out && pos + n <= cap) memcpy(out + pos, p, n);
+        pos += n;
+    }
+    void u64(uint64_t v) { bytes(&v, 8); }  // little-endian host
+    void u32(uint32_t v) { bytes(&v, 4); }
+    uint64_t reserve(size_t n) {  // returns the offset of a region filled later (D2H)
+        uint64_t at = pos;
+        pos += n;
+        return at;
+    }
+    bool fits() const { return out && pos <= cap; }
+};
+
+template <class F>
+struct FriRoundDev {
+    typename F::T* poly = nullptr;   // D planes x npad
+    typename F::T* cw = nullptr;     // D planes x domain
+    uint32_t* nodes = nullptr;       // (2,2) tree, domain - 1 digests
+    uint64_t npad = 0, domain = 0, len = 0;
+    uint8_t root[32];
+};
+
+template <class F>
+static void ser_ext(ProofWriter& w, const Ext<F>& e) {
+    w.bytes(e.c, sizeof(typename F::T) * F::D);  // ark compressed: LE, ceil(bits/8) bytes per coordinate
 }
+
+// upper bound of the proof dump size for a given shape (so callers can allocate once)
+template <class F>
+uint64_t proof_size_bound(const ms_stark_params& p, const StarkDerived& d, uint64_t n, uint64_t cols) {
+    const uint64_t E = sizeof(typename F::T) * F::D;
+    uint64_t sz = 8 + 8 + 8 + 64 * d.rounds + 64 + 16 + d.constrain_queries * cols * E + 8 + d.constrain_queries * E + 8;
+    uint64_t npad = n, domain = n * p.blowup_factor;
+    for (uint64_t i = 0; i + 1 < d.rounds; i++) {
+        uint64_t path_len = domain >= 2 ? (uint64_t)ilog2(domain / 2) : 0;
+        uint64_t per_q = 6 * E + 2 * (8 + 2 * E + 8 + path_len * (8 + 64)) + 8 + npad * E;
+        sz += 8 + d.fri_queries * per_q;
+        npad = npad > 1 ? npad / 2 : 1;
+        domain /= 2;
+    }
+    return sz;
+}
+
+template <class F>
+int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* trace_rm_host, const void* d_trace_cm_in,
+                uint64_t n, uint64_t w, const typename F::T* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
+    using T = typename F::T;
+    using E = Ext<F>;
+    constexpr int D = F::D;
+    ps->timings.clear();
+    if (!proof_len) return fail(c, MS_ERR_BAD_SHAPE, "proof_len is null");
+    StarkDerived der;
+    if (stark_derive(F::ID, p, &der) != MS_OK) return fail(c, MS_ERR_BAD_SHAPE, "bad STARK parameters (starks.rs:317-320)");
+    // TraceTable::new pads to next_pow2(steps + 1) rows (air.rs:74)
+    uint64_t want_n = 1;
+    while (want_n < p.steps + 1) want_n <<= 1;
+    if (n != want_n || w == 0) return fail(c, MS_ERR_BAD_SHAPE, "trace must have next_pow2(steps+1) = %llu rows, got %llu", (unsigned long long)want_n, (unsigned long long)n);
+    const uint64_t C = w + t, B = p.blowup_factor, L = B * n;
+    const uint64_t lpn = p.trace_columns, kk = p.inner_children ? p.inner_children : 2;
+    const uint64_t R = der.rounds, Q = der.constrain_queries, QF = der.fri_queries;
+    const uint64_t bound = proof_size_bound<F>(p, der, n, C);
+    if (!proof_out || *proof_len < bound) {
+        *proof_len = bound;
+        return fail(c, MS_ERR_BUFFER_TOO_SMALL, "proof buffer needs %llu bytes", (unsigned long long)bound);
+    }
+    StageTimer tm(c, ps);
+    IOPattern io = stark_iopattern(F::BITS, D, R, Q, QF);
+    Merlin merlin(io, c->bridge_masks);
+    const size_t cb = (F::BITS + 128) / 8;
+    auto challenge_base = [&](T* out) -> bool {
+        uint8_t buf[32];
+        if (!merlin.challenge_bytes(buf, cb)) return false;
+        *out = (T)be_bytes_mod(buf, cb, (uint64_t)F::P);
+        return true;
+    };
+    auto challenge_ext = [&](E* out) -> bool {
+        uint8_t buf[32 * 4];
+        if (!merlin.challenge_bytes(buf, cb * D)) return false;
+        for (int d = 0; d < D; d++) out->c[d] = (T)be_bytes_mod(buf + d * cb, cb, (uint64_t)F::P);
+        return true;
+    };
+#define TR(expr) do { if (!(expr)) return fail(c, MS_ERR_TRANSCRIPT, "transcript pattern violated at %s", #expr); } while (0)
+
+    // ---- 1.1 trace on the device (column-major) and its commitment           starks.rs:68-73
+    tm.begin("upload+transpose");
+    Scratch trace_cm(c), trace_rm(c);
+    const T* d_trace = reinterpret_cast<const T*>(d_trace_cm_in);
+    if (!d_trace) {
+        MS_TRY(trace_rm.alloc(n * w * sizeof(T)));
+        MS_TRY(trace_cm.alloc(n * w * sizeof(T)));
+        MS_CUDA(c, cudaMemcpyAsync(trace_rm.p, trace_rm_host, n * w * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        MS_TRY(transpose<F>(c, trace_rm.as<T>(), trace_cm.as<T>(), n, w, true));
+        d_trace = trace_cm.as<T>();
+    }
+    tm.end();
+    tm.begin("trace_commit");
+    uint8_t trace_root[32], lde_root[32];
+    MS_TRY(merkle_commit<F>(c, d_trace, n, n, w, 1, lpn, kk, nullptr, trace_root));
+    tm.end();
+    TR(merlin.add_bytes(trace_root, 32));
+    // ---- 1.2 LDE of trace + constraint polynomials and its commitment            starks.rs:80-95
+    T shift;
+    TR(challenge_base(&shift));
+    if (shift == 0) return fail(c, MS_ERR_BAD_SHAPE, "random_shift is zero (get_coset unwrap, starks.rs:84-85)");
+    Scratch coeffs(c), lde(c);
+    MS_TRY(coeffs.alloc((C + 1) * n * sizeof(T)));  // C constraint columns + the mixed polynomial
+    tm.begin("intt");
+    MS_TRY(lde_batch<F>(c, d_trace, n, w, ilog2(n), 0, (T)1, true, coeffs.as<T>(), n));  // air.rs:147-160
+    tm.end();
+    tm.begin("constraints");
+    MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
+    tm.end();
+    MS_TRY(lde.alloc(C * L * sizeof(T)));
+    tm.begin("lde");
+    MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, C, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91
+    tm.end();
+    tm.begin("lde_commit");
+    MS_TRY(merkle_commit<F>(c, lde.as<T>(), L, L, C, 1, lpn, kk, nullptr, lde_root));  // starks.rs:92-94
+    tm.end();
+    TR(merlin.add_bytes(lde_root, 32));
+    cudaFreeAsync(lde.p, c->stream);  // the LDE tree is never opened by the reference
+    lde.p = nullptr;
+    // ---- 1.3 mixing                                                                  starks.rs:108-119
+    T r;
+    TR(challenge_base(&r));
+    T* d_mixed = coeffs.as<T>() + C * n;
+    tm.begin("mix");
+    MS_TRY(mix<F>(c, coeffs.as<T>(), n, n, C, r, d_mixed));
+    tm.end();
+    // divide_by_vanishing_poly yields (quotient, remainder); the reference asserts quotient == 0,
+    // which holds for any polynomial with <= N coefficients, and carries the remainder (= mixed) on.
+    // ---- 2. DEEP-ALI queries                                                         starks.rs:124-151
+    std::vector<E> zq(Q);
+    for (uint64_t q = 0; q < Q; q++) TR(challenge_ext(&zq[q]));
+    std::vector<E> opens(Q * (C + 1));
+    tm.begin("deep_open");
+    MS_TRY(eval_points<F>(c, coeffs.as<T>(), n, 0, 1, n, 1, C + 1, zq.data(), (int)Q, opens.data()));
+    tm.end();
+    // ---- 3. FRI commit phase                                                        fri.rs:64-113
+    tm.begin("fri_commit_phase");
+    std::vector<FriRoundDev<F>> rounds(R);
+    std::vector<Scratch> keep;
+    keep.reserve(4 * R + 8);
+    auto dev_alloc = [&](size_t bytes, void** out) -> int {
+        keep.emplace_back(c);
+        MS_TRY(keep.back().alloc(bytes));
+        *out = keep.back().p;
+        return MS_OK;
+    };
+    Scratch d_len(c);
+    MS_TRY(d_len.alloc(8));
+    auto poly_len = [&](const T* planes, uint64_t stride, int nplanes, uint64_t npad, uint64_t* out) -> int {
+        MS_CUDA(c, cudaMemsetAsync(d_len.p, 0, 8, c->stream));
+        k_poly_len<F><<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(planes, stride, nplanes, npad, d_len.as<unsigned long long>());
+        MS_LAUNCH_CHECK(c);
+        unsigned long long v = 0;
+        MS_CUDA(c, cudaMemcpyAsync(&v, d_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        *out = v;
+        return MS_OK;
+    };
+    {
+        // round 0: the mixed polynomial lifted to the extension (field.rs:23-32): upper planes zero.
+        uint64_t len0 = 0;
+        MS_TRY(poly_len(d_mixed, n, 1, n, &len0));
+        uint64_t deg = len0 ? len0 - 1 : 0;  // ark: degree() of the zero polynomial is 0
+        uint64_t npad = 1;
+        while (npad < deg + 1) npad <<= 1;  // Radix2EvaluationDomain::new((deg+1)*B) rounds up (fri.rs:74,315)
+        FriRoundDev<F>& r0 = rounds[0];
+        r0.npad = npad;
+        r0.domain = npad * B;
+        r0.len = len0;
+        MS_TRY(dev_alloc(D * npad * sizeof(T), (void**)&r0.poly));
+        MS_CUDA(c, cudaMemsetAsync(r0.poly, 0, D * npad * sizeof(T), c->stream));
+        MS_CUDA(c, cudaMemcpyAsync(r0.poly, d_mixed, npad * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    for (uint64_t i = 0; i < R; i++) {
+        FriRoundDev<F>& cur = rounds[i];
+        if (i > 0) {
+            FriRoundDev<F>& prev = rounds[i - 1];
+            E z, alpha, deep[2];
+            TR(challenge_ext(&z));                                                      // fri.rs:89
+            MS_TRY(fri_deep_coeffs<F>(c, prev.poly, prev.npad, prev.npad, z.c, deep[0].c));  // fri.rs:90
+            uint8_t dbytes[2 * 4 * 8];
+            memcpy(dbytes, deep, 2 * sizeof(E));
+            TR(merlin.add_bytes(dbytes, 2 * sizeof(E)));                                // fri.rs:94
+            TR(challenge_ext(&alpha));                                                  // fri.rs:96
+            cur.npad = prev.npad > 1 ? prev.npad / 2 : 1;
+            cur.domain = prev.domain / 2;                                               // fri.rs:374-376
+            if (cur.domain < 2) return fail(c, MS_ERR_BAD_SHAPE, "FRI domain exhausted at round %llu (merkle.rs:93-104 would panic)", (unsigned long long)i);
+            MS_TRY(dev_alloc(D * cur.npad * sizeof(T), (void**)&cur.poly));
+            MS_CUDA(c, cudaMemsetAsync(cur.poly, 0, D * cur.npad * sizeof(T), c->stream));
+            MS_TRY(fri_fold<F>(c, prev.poly, prev.npad, prev.npad, z.c, alpha.c, deep[0].c, cur.poly, cur.npad));  // fri.rs:97-101
+            MS_TRY(poly_len(cur.poly, cur.npad, D, cur.npad, &cur.len));
+        }
+        MS_TRY(dev_alloc(D * cur.domain * sizeof(T), (void**)&cur.cw));
+        MS_TRY(dev_alloc((cur.domain - 1) * 32, (void**)&cur.nodes));
+        MS_TRY(fri_commit<F>(c, cur.poly, cur.npad, cur.domain, cur.domain / cur.npad, cur.cw, cur.domain, cur.nodes, cur.root));  // fri.rs:345-352
+        if (i > 0) TR(merlin.add_bytes(cur.root, 32));                                  // fri.rs:107-108 (round 0 is not absorbed)
+    }
+    tm.end();
+    // ---- FRI query phase                                                            fri.rs:115-189
+    tm.begin("fri_query_phase");
+    std::vector<uint8_t> braw(8 * QF);
+    TR(merlin.challenge_bytes(braw.data(), braw.size()));                               // fri.rs:121-122
+    std::vector<uint64_t> betas(QF);
+    for (uint64_t k = 0; k < QF; k++) memcpy(&betas[k], &braw[8 * k], 8);               // usize::from_le_bytes
+    // ---- serialise the fixed part (field order of starks.rs:21-28)
+    ProofWriter pw(proof_out, *proof_len);
+    pw.bytes("MSTARKP1", 8);
+    pw.u32((uint32_t)F::ID);
+    pw.u32((uint32_t)D);
+    pw.u64(merlin.transcript.size());
+    pw.bytes(merlin.transcript.data(), merlin.transcript.size());
+    pw.bytes(trace_root, 32);
+    pw.bytes(lde_root, 32);
+    pw.u64(Q);
+    pw.u64(Q ? C : 0);
+    for (uint64_t q = 0; q < Q; q++)
+        for (uint64_t col = 0; col < C; col++) ser_ext<F>(pw, opens[q * (C + 1) + col]);
+    pw.u64(Q);
+    for (uint64_t q = 0; q < Q; q++) ser_ext<F>(pw, opens[q * (C + 1) + C]);
+    pw.u64(R - 1);
+    struct PendingCopy { uint64_t at; const void* src; size_t bytes; };
+    std::vector<PendingCopy> copies;
+    for (uint64_t i = 0; i + 1 < R; i++) {
+        FriRoundDev<F>& prev = rounds[i];
+        FriRoundDev<F>& nxt = rounds[i + 1];
+        const uint64_t nd = prev.domain;
+        const T g_prev = root_of_unity<F>(ilog2(nd)), g_next = root_of_unity<F>(ilog2(nxt.domain));
+        std::vector<unsigned long long> idx(3 * QF);
+        std::vector<T> x1(QF), x2(QF), x3(QF), s2(QF);
+        for (uint64_t k = 0; k < QF; k++) {
+            uint64_t beta = betas[k];
+            if (beta > nd) beta %= nd;                                                   // fri.rs:144 (strict >)
+            x1[k] = fpow<F>(g_prev, beta);                                               // fri.rs:148
+            x2[k] = fpow<F>(g_prev, nxt.domain + beta);                                  // fri.rs:149
+            x3[k] = fpow<F>(g_next, beta);                                               // fri.rs:150
+            s2[k] = F::mul(x1[k], x1[k]);
+            idx[3 * k] = beta % nd;
+            idx[3 * k + 1] = (nxt.domain + beta) % nd;
+            idx[3 * k + 2] = beta % nxt.domain;
+        }
+        // y1, y2 = prev.poly(x1), prev.poly(x2); y3 = round.poly(x3): evaluations at domain points are
+        // codeword entries (exact arithmetic), so they are gathered instead of re-evaluated.
+        Scratch d_idx(c), d_ys(c), d_found(c), d_neigh_idx(c), d_neigh(c), d_paths(c);
+        MS_TRY(d_idx.alloc(idx.size() * 8));
+        MS_TRY(d_ys.alloc(3 * QF * sizeof(E)));
+        std::vector<E> ys(3 * QF);
+        {
+            // gather y1,y2 from prev.cw and y3 from nxt.cw: two launches over interleaved indices
+            std::vector<unsigned long long> i12(2 * QF), i3(QF);
+            for (uint64_t k = 0; k < QF; k++) { i12[2 * k] = idx[3 * k]; i12[2 * k + 1] = idx[3 * k + 1]; i3[k] = idx[3 * k + 2]; }
+            MS_CUDA(c, cudaMemcpyAsync(d_idx.p, i12.data(), i12.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            MS_CUDA(c, cudaMemcpyAsync(d_idx.as<unsigned long long>() + 2 * QF, i3.data(), i3.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(prev.cw, prev.domain, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys.as<E>());
+            MS_LAUNCH_CHECK(c);
+            k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(nxt.cw, nxt.domain, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys.as<E>() + 2 * QF);
+            MS_LAUNCH_CHECK(c);
+        }
+        // openings by value search: first leaf equal to y (merkle.rs:216-225), for y1 and y2 of each query
+        MS_TRY(d_found.alloc(2 * QF * 8));
+        MS_CUDA(c, cudaMemsetAsync(d_found.p, 0xff, 2 * QF * 8, c->stream));
+        k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(prev.cw, prev.domain, nd, d_ys.as<E>(), (int)(2 * QF), d_found.as<unsigned long long>());
+        MS_LAUNCH_CHECK(c);
+        std::vector<unsigned long long> found(2 * QF);
+        MS_CUDA(c, cudaMemcpyAsync(ys.data(), d_ys.p, 3 * QF * sizeof(E), cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaMemcpyAsync(found.data(), d_found.p, 2 * QF * 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (auto f : found)
+            if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
+        const int path_len = ilog2(nd / 2);
+        std::vector<unsigned long long> nidx(4 * QF);
+        for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = found[k] & ~1ULL; nidx[2 * k + 1] = found[k] | 1ULL; }
+        MS_TRY(d_neigh_idx.alloc(nidx.size() * 8));
+        MS_TRY(d_neigh.alloc(4 * QF * sizeof(E)));
+        MS_TRY(d_paths.alloc((size_t)2 * QF * (path_len ? path_len : 1) * 64));
+        MS_CUDA(c, cudaMemcpyAsync(d_neigh_idx.p, nidx.data(), nidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(prev.cw, prev.domain, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh.as<E>());
+        MS_LAUNCH_CHECK(c);
+        std::vector<uint32_t> paths((size_t)2 * QF * path_len * 16);
+        if (path_len) {
+            int total = (int)(2 * QF) * path_len * 16;
+            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(prev.nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
+            MS_LAUNCH_CHECK(c);
+            MS_CUDA(c, cudaMemcpyAsync(paths.data(), d_paths.p, paths.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        std::vector<E> neigh(4 * QF);
+        MS_CUDA(c, cudaMemcpyAsync(neigh.data(), d_neigh.p, 4 * QF * sizeof(E), cudaMemcpyDeviceToHost, c->stream));
+        // quotients (fri.rs:157-167)
+        const uint64_t nq = prev.len >= 3 ? prev.len - 2 : 0;
+        T* d_quot = nullptr;
+        if (nq) {
+            MS_TRY(dev_alloc((size_t)QF * nq * sizeof(E), (void**)&d_quot));
+            MS_TRY(fri_query_quotients<F>(c, prev.poly, prev.npad, prev.len, s2.data(), (uint32_t)QF, d_quot));
+        }
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        // ---- serialise this round (fri.rs:18-22, merkle.rs:293-298)
+        pw.u64(QF);
+        for (uint64_t k = 0; k < QF; k++) {
+            E pts[6] = {ext_from_base<F>(x1[k]), ys[2 * k], ext_from_base<F>(x2[k]), ys[2 * k + 1], ext_from_base<F>(x3[k]), ys[2 * QF + k]};
+            for (int e = 0; e < 6; e++) ser_ext<F>(pw, pts[e]);
+            for (int which = 0; which < 2; which++) {
+                uint64_t m = 2 * k + which;
+                pw.u64(2);
+                ser_ext<F>(pw, neigh[2 * m]);
+                ser_ext<F>(pw, neigh[2 * m + 1]);
+                pw.u64(path_len);
+                for (int l = 0; l < path_len; l++) {
+                    pw.u64(2);
+                    for (int s = 0; s < 2; s++) {
+                        uint8_t dg[32];
+                        digest_words_to_bytes(&paths[((size_t)m * path_len + l) * 16 + s * 8], dg);
+                        pw.bytes(dg, 32);
+                    }
+                }
+            }
+            pw.u64(nq);
+            if (nq) copies.push_back({pw.reserve(nq * sizeof(E)), d_quot + (size_t)k * nq * D, (size_t)(nq * sizeof(E))});
+        }
+    }
+    if (!pw.fits()) {
+        *proof_len = pw.pos;
+        return fail(c, MS_ERR_BUFFER_TOO_SMALL, "proof buffer needs %llu bytes", (unsigned long long)pw.pos);
+    }
+    for (auto& cp : copies) MS_CUDA(c, cudaMemcpyAsync(proof_out + cp.at, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    tm.end();
+    *proof_len = pw.pos;
+#undef TR
+    return MS_OK;
+}
+
+}  // namespace ms
