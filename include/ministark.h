@@ -57,6 +57,11 @@ const char* ms_last_error(const ms_ctx* ctx);
 int32_t ms_sync(ms_ctx* ctx);
 /* kernels launched by this library on this context since creation (bench.py gpu_launches) */
 uint64_t ms_launch_count(const ms_ctx* ctx);
+/* Per-kernel device timing for roofline reports: when on, the LDE / Merkle kernels are bracketed by
+ * CUDA events on the context's stream; ms_profile_collect synchronises, sums the elapsed time and the
+ * launch count per kernel name (static strings) since the last collect, and returns the entry count. */
+int32_t ms_set_profiling(ms_ctx* ctx, int32_t on);
+int32_t ms_profile_collect(ms_ctx* ctx, const char** names, float* total_ms, uint32_t* counts, int32_t cap);
 /* Display of the zero element: 0 -> "0" (ark-ff 0.5.0, default), 1 -> "" (ark-ff 0.4.x) */
 int32_t ms_set_zero_display(ms_ctx* ctx, int32_t empty);
 

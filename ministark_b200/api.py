@@ -67,6 +67,17 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.ms_launch_count(self.h))
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.ms_set_profiling(self.h, int(on)))
+
+    def profile_collect(self):
+        """{kernel name: (total device ms, launches)} since the last collect."""
+        names = (C.c_char_p * 64)()
+        ms_ = (C.c_float * 64)()
+        cnt = (C.c_uint32 * 64)()
+        n = self.lib.ms_profile_collect(self.h, names, ms_, cnt, 64)
+        return {names[i].decode(): (float(ms_[i]), int(cnt[i])) for i in range(n)}
+
     def set_zero_display(self, empty: bool):
         self._check(self.lib.ms_set_zero_display(self.h, int(empty)))
 

@@ -21,6 +21,10 @@ struct Ctx {
     int zero_display_empty = 0;  // ark-ff 0.4 printed "" for zero; 0.5.0 prints "0" 
     void* wtab[2] = {nullptr, nullptr};  // plain DIT twiddles, forward / inverse (see ntt.cuh)
     unsigned long long launches = 0;     // kernels launched by this library (bench gpu_launches)
+    // optional per-kernel device timing (bench.py roofline): event pairs collected by ms_profile_collect
+    bool profile = false;
+    struct ProfEntry { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfEntry> prof;
     // transcript switches (host prover)
     uint8_t bridge_masks[3] = {0x00, 0x01, 0x02};
 };
@@ -82,6 +86,19 @@ struct Scratch {
     template <class T>
     T* as() { return reinterpret_cast<T*>(p); }
 };
+
+inline void prof_begin(Ctx* c, const char* name) {
+    if (!c->profile) return;
+    Ctx::ProfEntry e{name, nullptr, nullptr};
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, c->stream);
+    c->prof.push_back(e);
+}
+inline void prof_end(Ctx* c) {
+    if (!c->profile || c->prof.empty()) return;
+    cudaEventRecord(c->prof.back().b, c->stream);
+}
 
 inline int ilog2(uint64_t v) {
     int l = 0;

@@ -243,8 +243,10 @@ int merkle_commit(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t
         d_nodes = own.as<uint32_t>();
     }
     unsigned blocks = (unsigned)((n1 + LEAF_THREADS - 1) / LEAF_THREADS);
+    prof_begin(c, "k_leaf_hash");
     if (deg == 1) k_leaf_hash<F, 1><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
     else k_leaf_hash<F, F::D><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
+    prof_end(c);
     MS_LAUNCH_CHECK(c);
     uint64_t src = 0, lv = n1;
     while (lv > 1) {
@@ -252,12 +254,14 @@ int merkle_commit(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t
         const uint32_t* ch = d_nodes + src * 8;
         uint32_t* pa = d_nodes + (src + lv) * 8;
         unsigned nb = (unsigned)((np + 255) / 256);
+        prof_begin(c, "k_node_hash");
         switch (k) {
             case 2: k_node_hash<2><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
             case 4: k_node_hash<4><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
             case 8: k_node_hash<8><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
             default: k_node_hash<16><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
         }
+        prof_end(c);
         MS_LAUNCH_CHECK(c);
         src += lv;
         lv = np;

@@ -76,6 +76,34 @@ int32_t ms_sync(ms_ctx* c) {
     return MS_OK;
 }
 uint64_t ms_launch_count(const ms_ctx* c) { return c ? c->launches : 0; }
+int32_t ms_set_profiling(ms_ctx* c, int32_t on) {
+    c->profile = on != 0;
+    return MS_OK;
+}
+int32_t ms_profile_collect(ms_ctx* c, const char** names, float* total_ms, uint32_t* counts, int32_t cap) {
+    cudaStreamSynchronize(c->stream);
+    int n = 0;
+    for (auto& e : c->prof) {
+        float t = 0;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+        int k = 0;
+        for (; k < n; k++)
+            if (names[k] == e.name) break;
+        if (k == n) {
+            if (n >= cap) continue;
+            names[n] = e.name;
+            total_ms[n] = 0;
+            counts[n] = 0;
+            n++;
+        }
+        total_ms[k] += t;
+        counts[k]++;
+    }
+    c->prof.clear();
+    return n;
+}
 int32_t ms_set_zero_display(ms_ctx* c, int32_t empty) {
     c->zero_display_empty = empty ? 1 : 0;
     return MS_OK;

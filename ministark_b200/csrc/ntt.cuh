@@ -281,7 +281,9 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     MS_TRY(t1.alloc(((size_t)B << pl.a) * sizeof(T)));
     if (pl.a > 0) {
         int n = B << pl.a;
+        prof_begin(c, "k_build_t1");
         k_build_t1<F><<<(n + 255) / 256, 256, 0, c->stream>>>(t1.as<T>(), wtab, d_sbase, pl.a, B);
+        prof_end(c);
         MS_LAUNCH_CHECK(c);
     }
     const bool two = pl.b > 0;
@@ -289,7 +291,9 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         MS_TRY(ft.alloc(((size_t)N << logB) * sizeof(T)));
         int chunk_log = pl.a < 6 ? pl.a : 6;
         uint64_t threads = (((uint64_t)1 << pl.b) << logB) * ((1ULL << pl.a) >> chunk_log);
+        prof_begin(c, "k_build_ft");
         k_build_ft<F><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(ft.as<T>(), d_shifts, wN, scale, pl.a, pl.b, logB, chunk_log);
+        prof_end(c);
         MS_LAUNCH_CHECK(c);
         MS_TRY(tmp.alloc(cols * ((size_t)N << logB) * sizeof(T)));
     }
@@ -299,16 +303,20 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         dim3 grid((unsigned)cols, (unsigned)((1ULL << pl.b) >> pl.logR1));
         T* o = two ? tmp.as<T>() : d_out;
         uint64_t os = two ? ((uint64_t)N << logB) : out_stride;
+        prof_begin(c, "k_lde_pass1");
         k_lde_pass1<F><<<grid, NTT_THREADS, smem, c->stream>>>(d_in, in_stride, o, os, t1.as<T>(), two ? ft.as<T>() : nullptr,
                                                                pl.a, pl.b, logB, pl.logR1, scale);
+        prof_end(c);
         MS_LAUNCH_CHECK(c);
     }
     if (two) {
         size_t smem = ((size_t)sizeof(T) << pl.b) << (pl.logR2 + logB);
         MS_CUDA(c, cudaFuncSetAttribute(k_lde_pass2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)cols, (unsigned)((1ULL << pl.a) >> pl.logR2));
+        prof_begin(c, "k_lde_pass2");
         k_lde_pass2<F><<<grid, NTT_THREADS, smem, c->stream>>>(tmp.as<T>(), (uint64_t)N << logB, d_out, out_stride, wtab,
                                                                pl.a, pl.b, logB, pl.logR2);
+        prof_end(c);
         MS_LAUNCH_CHECK(c);
     }
     return MS_OK;

@@ -39,7 +39,19 @@ static inline u64 gl_add(u64 a, u64 b) {
     return s;
 }
 static inline u64 gl_sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
-static inline u64 gl_mul(u64 a, u64 b) { return (u64)(((u128)a * b) % GL_P); }
+/* 128-bit product reduced with 2^64 = 2^32 - 1 and 2^96 = -1 (mod p); same value as (a*b) % p */
+static inline u64 gl_mul(u64 a, u64 b) {
+    u128 x = (u128)a * b;
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    u64 t0 = lo - hh;
+    if (lo < hh) t0 -= 0xFFFFFFFFULL;
+    u64 t1 = (hl << 32) - hl;
+    u64 r = t0 + t1;
+    if (r < t1) r += 0xFFFFFFFFULL;
+    return r >= GL_P ? r - GL_P : r;
+}
+static inline u64 gl_mul_slow(u64 a, u64 b) { return (u64)(((u128)a * b) % GL_P); }
 
 /* ------------------------------------------------------------------ BabyBear */
 #define BB_P 2013265921ULL
