@@ -6,35 +6,177 @@
 //   lde_batch:  out[c][B*k + j] = sum_{m<N} in[c][m] * (s_j * w^k)^m ,   s_j = shift * w_L^j ,
 //               k in [0,N), j in [0,B)          (B = 1, shift = 1, w = w_N^-1, scale = 1/N: iNTT)
 //
-// i.e. the size-L evaluation on the coset is done as B coset transforms of size N (the zero padded
-// size-L transform's first log2 B stages are pure replication).  N = n1 * n2 is split in at most
-// two passes over HBM; inside a pass a CTA owns a shared-memory tile and runs decimation-in-time
-// butterflies on it:
+// i.e. the size-L evaluation on the coset is B coset transforms of size N (the first log2 B stages
+// of the zero padded size-L transform are pure replication and are never executed).
 //
-//   pass 1  (stages 0..a-1, n2 = 2^a):  tile = [n2 strided rows] x [R consecutive m1] x [B cosets].
-//           The coset shift is folded into the stage twiddles t1[j][2^u+q] = s_j^(N/2^(u+1)) w_(2^(u+1))^q
-//           (no separate "distribute powers" pass), inputs are replicated B times on load, and the
-//           inter-pass factor ft = scale * (s_j w_N^k2)^m1 is applied on store.
-//   pass 2  (stages a..logN-1, n1 = 2^b): tile = contiguous block of R2 * n1 * B elements of the
-//           intermediate; plain twiddles; stores runs of R2*B consecutive output rows.
+// Work decomposition.  N = n1 * n2 (n2 = 2^a, n1 = 2^b) is covered by at most two passes over
+// HBM; both passes run the same kernel, k_ntt_tile, on a "tile" = [2^a' points] x [2^beta batch
+// entries] that lives in shared memory (8192 or 16384 elements):
 //
-// Intermediate and output share one index map, ((m1 + n1*k2)*B + j), which degenerates to the
-// natural output order when n1 = 1 (single pass).  Bit reversal is never a pass of its own: tiles
-// are loaded into shared memory in bit-reversed transform order.
+//   pass 1  transform along m2 (stride n1 in the input) for R consecutive m1 and all B cosets.
+//           The coset shift is folded into the stage twiddles t1[j][2^s+q] = s_j^(N/2^(s+1)) w_(2^(s+1))^q
+//           (no "distribute powers" pass), the B replicas are made on load, and the inter-pass
+//           factor ft = scale * s_j^m1 * w_N^(m1 k2) is applied on store.
+//   pass 2  transform along m1 for R2 consecutive k2 and all B cosets; plain twiddles; natural-order
+//           output.  With R = 1 the intermediate has the index map of the output and pass 2 runs
+//           in place (no temporary: the 2^24 x 64 LDE needs no second 32 GiB buffer).
+//
+// Inside a tile the log2(points) DIT stages are grouped in rounds of G <= 4 stages.  In a round a
+// thread owns "slots" of 2^G elements whose positions differ in the round's G bits, keeps them in
+// registers for the G stages, and only touches shared memory at round boundaries (XOR-swizzled, so
+// both the contiguous and the strided access patterns are bank-conflict free).  The first round
+// loads straight from HBM into registers (bit-reversed gather), the last one stores straight to
+// HBM, so a tile costs ceil(a/4) - 1 shared-memory exchanges instead of one per stage.
+//
+// Arithmetic (Goldilocks): butterflies run on lazily reduced values.  mul() returns a canonical
+// product, add()/sub() take (lazy, canonical) and return lazy values in [0, 2^64); carries are
+// folded back with 2^64 = 2^32 - 1 (mod p) through PTX carry chains (see Fast<GL>).  Everything
+// written to HBM is canonical.  BabyBear keeps canonical data and Montgomery-form twiddles.
 #pragma once
 #include "common.cuh"
 #include "field.cuh"
 
 namespace ms {
 
-constexpr int NTT_MAXLOG = 14;       // largest in-tile transform (plain twiddle table size)
-constexpr int NTT_LOG_TILE_PREF = 13;  // preferred tile: 8192 elements (64 KB Goldilocks)
+constexpr int NTT_MAXLOG = 14;         // largest in-tile transform (plain twiddle table size)
+constexpr int NTT_LOG_TILE_PREF = 13;  // preferred tile: 8192 elements (64 KB Goldilocks, 2 CTAs / SM)
 constexpr int NTT_LOG_TILE_MAX = 14;   // 128 KB Goldilocks tile, one CTA per SM
-constexpr int NTT_THREADS = 512;
+constexpr int NTT_THREADS = 256;
+constexpr int NTT_MAXG = 4;            // stages per round: 16 elements in registers
 
-__device__ __forceinline__ uint32_t brev_bits(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
+#ifdef __CUDA_ARCH__
+#define MS_LDG(p) __ldg(p)
+#else
+#define MS_LDG(p) (*(p))
+#endif
 
-// plain DIT twiddles W[2^u + q] = g_(2^(u+1))^q, u < NTT_MAXLOG, g_(2^(u+1)) = (inverse) root of unity
+MS_HD uint32_t brev_bits(uint32_t x, int bits) {
+#ifdef __CUDA_ARCH__
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Butterfly arithmetic.  Contract: mul(x: any representative, w: twiddle form) -> canonical;
+// add/sub(a: lazy, t: canonical) -> lazy; canon(lazy) -> canonical; to_tw(canonical) -> twiddle form.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+struct Fast;
+
+template <>
+struct Fast<GL> {
+    using T = uint64_t;
+    static MS_HD T to_tw(T w) { return w; }
+    static MS_HD T mul(T a, T b) {
+#ifdef __CUDA_ARCH__
+        // 128-bit product c3..c0, then c0 + c1 2^32 + c2 (2^32 - 1) - c3 with every carry folded
+        // back once; the last fold also subtracts p when the sum landed in [p, 2^64).
+        uint32_t r0, r1;
+        asm("{\n\t"
+            ".reg .u32 c0, c1, c2, c3, m, k, d;\n\t"
+            "mul.lo.u32 c0, %2, %4;\n\t"
+            "mul.hi.u32 c1, %2, %4;\n\t"
+            "mad.lo.cc.u32 c1, %2, %5, c1;\n\t"
+            "madc.hi.u32 c2, %2, %5, 0;\n\t"
+            "mad.lo.cc.u32 c1, %3, %4, c1;\n\t"
+            "madc.hi.cc.u32 c2, %3, %4, c2;\n\t"
+            "addc.u32 c3, 0, 0;\n\t"
+            "mad.lo.cc.u32 c2, %3, %5, c2;\n\t"
+            "madc.hi.u32 c3, %3, %5, c3;\n\t"
+            "sub.cc.u32 c0, c0, c3;\n\t"
+            "subc.cc.u32 c1, c1, 0;\n\t"
+            "subc.u32 m, 0, 0;\n\t"
+            "sub.cc.u32 c0, c0, m;\n\t"
+            "subc.u32 c1, c1, 0;\n\t"
+            "mad.lo.cc.u32 c0, c2, 0xFFFFFFFF, c0;\n\t"
+            "madc.hi.cc.u32 c1, c2, 0xFFFFFFFF, c1;\n\t"
+            "addc.u32 k, 0, 0;\n\t"
+            "add.cc.u32 d, c0, 0xFFFFFFFF;\n\t"
+            "addc.cc.u32 d, c1, 0;\n\t"
+            "addc.u32 k, k, 0;\n\t"
+            "mad.lo.cc.u32 %0, k, 0xFFFFFFFF, c0;\n\t"
+            "madc.hi.u32 %1, k, 0xFFFFFFFF, c1;\n\t"
+            "}"
+            : "=r"(r0), "=r"(r1)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+        return ((uint64_t)r1 << 32) | r0;
+#else
+        return GL::mul(a % GL::P, b % GL::P);
+#endif
+    }
+    static MS_HD T add(T a, T t) {
+#ifdef __CUDA_ARCH__
+        uint32_t r0, r1;
+        asm("{\n\t.reg .u32 k, s0, s1;\n\t"
+            "add.cc.u32 s0, %2, %4;\n\t"
+            "addc.cc.u32 s1, %3, %5;\n\t"
+            "addc.u32 k, 0, 0;\n\t"
+            "mad.lo.cc.u32 %0, k, 0xFFFFFFFF, s0;\n\t"
+            "madc.hi.u32 %1, k, 0xFFFFFFFF, s1;\n\t}"
+            : "=r"(r0), "=r"(r1)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)t), "r"((uint32_t)(t >> 32)));
+        return ((uint64_t)r1 << 32) | r0;
+#else
+        T s = a + t;
+        return s < a ? s + GL::EPS : s;
+#endif
+    }
+    static MS_HD T sub(T a, T t) {
+#ifdef __CUDA_ARCH__
+        uint32_t r0, r1;
+        asm("{\n\t.reg .u32 m, s0, s1;\n\t"
+            "sub.cc.u32 s0, %2, %4;\n\t"
+            "subc.cc.u32 s1, %3, %5;\n\t"
+            "subc.u32 m, 0, 0;\n\t"
+            "sub.cc.u32 %0, s0, m;\n\t"
+            "subc.u32 %1, s1, 0;\n\t}"
+            : "=r"(r0), "=r"(r1)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)t), "r"((uint32_t)(t >> 32)));
+        return ((uint64_t)r1 << 32) | r0;
+#else
+        T d = a - t;
+        return a < t ? d - GL::EPS : d;
+#endif
+    }
+    static MS_HD T canon(T a) { return a >= GL::P ? a - GL::P : a; }
+};
+
+template <>
+struct Fast<BB> {
+    using T = uint32_t;
+    static constexpr uint32_t PINV = 2281701377u;  // p^-1 mod 2^32
+    static MS_HD T to_tw(T w) { return (T)((((uint64_t)w) << 32) % BB::P); }  // Montgomery form, R = 2^32
+    // REDC(x * w R): x any 32-bit value, result canonical
+    static MS_HD T mul(T x, T w) {
+        uint64_t t = (uint64_t)x * w;
+        uint32_t m = (uint32_t)t * PINV;
+#ifdef __CUDA_ARCH__
+        uint32_t u = (uint32_t)(t >> 32) - __umulhi(m, BB::P);
+#else
+        uint32_t u = (uint32_t)(t >> 32) - (uint32_t)(((uint64_t)m * BB::P) >> 32);
+#endif
+        uint32_t v = u + BB::P;
+        return u < v ? u : v;  // u in (-p, p): the wrapped negative is the larger unsigned value
+    }
+    static MS_HD T add(T a, T t) {
+        uint32_t s = a + t, v = s - BB::P;
+        return s < v ? s : v;
+    }
+    static MS_HD T sub(T a, T t) {
+        uint32_t d = a - t, v = d + BB::P;
+        return d < v ? d : v;
+    }
+    static MS_HD T canon(T a) { return a; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// twiddle tables (built on the device with the canonical field ops, stored in twiddle form)
+// ------------------------------------------------------------------------------------------------
+// plain DIT twiddles W[2^s + q] = g_(2^(s+1))^q, s < NTT_MAXLOG, g = (inverse) root of unity
 template <class F>
 __global__ void k_build_wtab(typename F::T* w, const typename F::T* roots /*[NTT_MAXLOG]*/) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,10 +184,10 @@ __global__ void k_build_wtab(typename F::T* w, const typename F::T* roots /*[NTT
     if (idx == 0) { w[0] = 0; return; }
     int u = 31 - __clz(idx);
     int q = idx - (1 << u);
-    w[idx] = fpow<F>(roots[u], (uint64_t)q);
+    w[idx] = Fast<F>::to_tw(fpow<F>(roots[u], (uint64_t)q));
 }
 
-// t1[j*n2 + 2^u + q] = sbase[j*a + u] * W[2^u + q]
+// t1[j*n2 + 2^s + q] = sbase[j*a + s] * W[2^s + q]     (sbase canonical, W in twiddle form)
 template <class F>
 __global__ void k_build_t1(typename F::T* t1, const typename F::T* wtab, const typename F::T* sbase, int a, int B) {
     int n2 = 1 << a;
@@ -57,117 +199,356 @@ __global__ void k_build_t1(typename F::T* t1, const typename F::T* wtab, const t
     t1[idx] = F::mul(sbase[j * a + u], wtab[e]);
 }
 
-// ft[((m1 + n1*k2) << logB) + j] = scale * s_j^m1 * wN^(m1*k2)
+// ft[(((tile << a) + k2) << beta) | rr << logB | j] = scale * s_j^m1 * wN^(m1*k2), m1 = tile*R + rr
 template <class F>
 __global__ void k_build_ft(typename F::T* ft, const typename F::T* shifts /*[B]*/, typename F::T wN, typename F::T scale,
-                           int a, int b, int logB, int chunk_log) {
+                           int a, int b, int logB, int logR, int chunk_log) {
     using T = typename F::T;
-    const uint64_t n1 = 1ULL << b;
-    const uint64_t lanes = n1 << logB;
+    const uint64_t lanes = (1ULL << b) << logB;  // (m1, j)
     uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t lane = gid % lanes, chunk = gid / lanes;
     uint64_t nchunks = (1ULL << a) >> chunk_log;
     if (chunk >= nchunks) return;
-    uint64_t m1 = lane >> logB;
-    int j = (int)(lane & ((1u << logB) - 1));
+    const uint64_t m1 = lane >> logB;
+    const int j = (int)(lane & ((1u << logB) - 1));
+    const uint64_t tile = m1 >> logR, rr = m1 & ((1u << logR) - 1);
+    const int beta = logR + logB;
     uint64_t k2 = chunk << chunk_log;
     T rho = fpow<F>(wN, m1);
     T v = F::mul(F::mul(scale, fpow<F>(shifts[j], m1)), fpow<F>(rho, k2));
     for (uint64_t i = 0; i < (1ULL << chunk_log); i++, k2++) {
-        ft[((m1 + n1 * k2) << logB) + j] = v;
+        ft[((((tile << a) + k2) << beta) | (rr << logB)) + j] = Fast<F>::to_tw(v);
         v = F::mul(v, rho);
     }
 }
 
-// shared-memory DIT stages [0, nst) on a tile laid out as S[(P << logRB) | beta]; the twiddle for
-// butterfly (stage u, index q, batch beta) is tw[(beta & jmask) * tw_jstride + 2^u + q].
+// ------------------------------------------------------------------------------------------------
+// the tile kernel
+// ------------------------------------------------------------------------------------------------
 template <class F>
-__device__ __forceinline__ void tile_dit(typename F::T* S, int nst, int logRB, const typename F::T* __restrict__ tw,
-                                         uint32_t jmask, uint32_t tw_jstride) {
+struct NttTile {
     using T = typename F::T;
-    const uint32_t half = (1u << nst) >> 1;
-    const uint32_t total = half << logRB;
-    const uint32_t RBm = (1u << logRB) - 1;
-    for (int u = 0; u < nst; u++) {
-        __syncthreads();
-        const uint32_t h = 1u << u;
-        for (uint32_t x = threadIdx.x; x < total; x += blockDim.x) {
-            uint32_t beta = x & RBm, bf = x >> logRB;
-            uint32_t q = bf & (h - 1);
-            uint32_t P = ((bf >> u) << (u + 1)) | q;
-            uint32_t i0 = (P << logRB) | beta, i1 = i0 + (h << logRB);
-            T w = __ldg(&tw[(beta & jmask) * tw_jstride + h + q]);
-            T A = S[i0];
-            T Bv = F::mul(S[i1], w);
-            S[i0] = F::add(A, Bv);
-            S[i1] = F::sub(A, Bv);
+    const T* src;
+    uint64_t src_stride;  // elements between columns
+    T* dst;
+    uint64_t dst_stride;
+    const T* tw;          // twiddle of (stage s, index q, batch b): tw[(b & jmask) * jstride + 2^s + q]
+    const T* ft;          // per-element factor indexed like dst (pass 1 of two), or nullptr
+    T scale;              // twiddle form; applied on store when ft == nullptr and has_scale
+    int has_scale;
+    int a;                // log2(points of the in-tile transform)
+    int beta;             // log2(batch entries per point)
+    int logB;             // the low logB bits of a batch index are the coset j
+    uint32_t jmask, jstride;
+    int mode;             // 0: first (or only) pass, 1: second pass
+    int bq;               // mode 0: log2(n1), the input stride of one transform step
+    int a1, beta1, logR1; // mode 1: geometry of the first pass (a1 = log2 n2)
+    uint32_t tiles;       // tiles per column
+    uint32_t cols;
+};
+
+// element index of (position P, batch b) of tile `tile` in the source / destination column
+template <class F>
+MS_HD uint64_t tile_src_index(const NttTile<F>& g, uint32_t tile, uint32_t P, uint32_t b) {
+    if (g.mode == 0) {
+        const int logR = g.beta - g.logB;
+        return ((uint64_t)tile << logR) + (b >> g.logB) + ((uint64_t)brev_bits(P, g.a) << g.bq);
+    }
+    const int logR2 = g.beta - g.logB;
+    const uint64_t m1 = brev_bits(P, g.a);
+    const uint64_t k2 = ((uint64_t)tile << logR2) + (b >> g.logB);
+    const uint32_t j = b & ((1u << g.logB) - 1);
+    return (((((m1 >> g.logR1) << g.a1) + k2) << g.beta1) | ((m1 & ((1u << g.logR1) - 1)) << g.logB)) + j;
+}
+template <class F>
+MS_HD uint64_t tile_dst_index(const NttTile<F>& g, uint32_t tile, uint32_t P, uint32_t b) {
+    if (g.mode == 0) return ((((uint64_t)tile << g.a) + P) << g.beta) | b;
+    const int logR2 = g.beta - g.logB;
+    const uint64_t k2 = ((uint64_t)tile << logR2) + (b >> g.logB);
+    const uint32_t j = b & ((1u << g.logB) - 1);
+    return ((((uint64_t)P << g.a1) + k2) << g.logB) | j;
+}
+
+// shared-memory swizzle: bijection on every aligned group of 2^(2*SW) elements; makes the strided
+// slot accesses of the u = 0 rounds and the contiguous accesses of the later rounds conflict free
+template <class F>
+MS_HD uint32_t tile_swz(uint32_t idx) {
+    constexpr int SW = sizeof(typename F::T) == 8 ? 4 : 5;  // elements per 128-byte bank row
+    return idx ^ ((idx >> SW) & ((1u << SW) - 1));
+}
+
+// rounds of a 2^a-point tile: ceil(a/4) rounds, sizes as even as possible, larger ones first
+MS_HD int tile_rounds(int a) { return (a + NTT_MAXG - 1) / NTT_MAXG; }
+MS_HD int tile_round_size(int a, int r) {
+    int nr = tile_rounds(a);
+    return a / nr + (r < a % nr ? 1 : 0);
+}
+
+// One slot of one round: stages [u, u+G) on the 2^G elements P0 + (r << u) of batch b.
+template <class F, int G>
+MS_HD void tile_slot(const NttTile<F>& g, typename F::T* S, const typename F::T* __restrict__ src, typename F::T* __restrict__ dst,
+                     uint32_t tile, uint32_t slot, int u, bool first, bool last) {
+    using T = typename F::T;
+    using A = Fast<F>;
+    constexpr int E = 1 << G;
+    const uint32_t b = slot & ((1u << g.beta) - 1), t = slot >> g.beta;
+    const uint32_t lo = t & ((1u << u) - 1), hi = t >> u;
+    const uint32_t P0 = lo + (hi << (u + G));
+    const T* __restrict__ twj = g.tw + (size_t)(b & g.jmask) * g.jstride + lo;
+    T w[E];  // w[2^s' + r'] = twiddle of local stage s', local index r'
+#pragma unroll
+    for (int s = 0; s < G; s++)
+#pragma unroll
+        for (int r = 0; r < (1 << s); r++) {
+#ifdef __CUDA_ARCH__
+            w[(1 << s) + r] = __ldg(&twj[(1u << (u + s)) + ((uint32_t)r << u)]);
+#else
+            w[(1 << s) + r] = twj[(1u << (u + s)) + ((uint32_t)r << u)];
+#endif
+        }
+    T v[E];
+    if (first) {
+#pragma unroll
+        for (int r = 0; r < E; r++) v[r] = src[tile_src_index<F>(g, tile, P0 + ((uint32_t)r << u), b)];
+    } else {
+#pragma unroll
+        for (int r = 0; r < E; r++) v[r] = S[tile_swz<F>(((P0 + ((uint32_t)r << u)) << g.beta) | b)];
+    }
+#pragma unroll
+    for (int s = 0; s < G; s++) {
+        const int h = 1 << s;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            if (r & h) continue;
+            T x = A::mul(v[r | h], w[h + (r & (h - 1))]);
+            T y = v[r];
+            v[r] = A::add(y, x);
+            v[r | h] = A::sub(y, x);
         }
     }
-    __syncthreads();
-}
-
-template <class F>
-__global__ void __launch_bounds__(NTT_THREADS)
-k_lde_pass1(const typename F::T* __restrict__ in, uint64_t in_stride, typename F::T* __restrict__ out, uint64_t out_stride,
-            const typename F::T* __restrict__ t1, const typename F::T* __restrict__ ft, int a, int b, int logB, int logR,
-            typename F::T scale) {
-    using T = typename F::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* S = reinterpret_cast<T*>(smem_raw);
-    const int logRB = logR + logB;
-    const uint32_t n2 = 1u << a;
-    const uint64_t n1 = 1ULL << b;
-    const uint64_t m1_0 = (uint64_t)blockIdx.y << logR;
-    const T* src = in + (uint64_t)blockIdx.x * in_stride;
-    T* dst = out + (uint64_t)blockIdx.x * out_stride;
-    const uint32_t tile = n2 << logRB;
-    const uint32_t Rm = (1u << logR) - 1;
-    // load: every coefficient is replicated over the B cosets (trivial first log2 B DIT levels);
-    // lanes of one replication group read the same address (single broadcast transaction)
-    for (uint32_t s = threadIdx.x; s < tile; s += blockDim.x) {
-        uint32_t r = (s >> logB) & Rm, P = s >> logRB;
-        uint64_t m2 = brev_bits(P, a);
-        S[s] = src[m1_0 + r + n1 * m2];
-    }
-    tile_dit<F>(S, a, logRB, t1, (1u << logB) - 1, n2);
-    const bool has_ft = ft != nullptr;
-    for (uint32_t s = threadIdx.x; s < tile; s += blockDim.x) {
-        uint32_t beta = s & ((1u << logRB) - 1);
-        uint64_t k2 = s >> logRB;
-        uint64_t g = ((m1_0 + n1 * k2) << logB) + beta;
-        T v = S[s];
-        if (has_ft) v = F::mul(v, __ldg(&ft[g]));
-        else if (scale != 1) v = F::mul(v, scale);
-        dst[g] = v;
+    if (last) {
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint64_t o = tile_dst_index<F>(g, tile, P0 + ((uint32_t)r << u), b);
+            T x = v[r];
+            if (g.ft) {
+#ifdef __CUDA_ARCH__
+                x = A::mul(x, __ldg(&g.ft[o]));
+#else
+                x = A::mul(x, g.ft[o]);
+#endif
+            } else if (g.has_scale) x = A::mul(x, g.scale);
+            else x = A::canon(x);
+            dst[o] = x;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < E; r++) S[tile_swz<F>(((P0 + ((uint32_t)r << u)) << g.beta) | b)] = v[r];
     }
 }
 
+// all slots of round `round` that thread `tid` of `nthreads` owns
 template <class F>
-__global__ void __launch_bounds__(NTT_THREADS)
-k_lde_pass2(const typename F::T* __restrict__ in, uint64_t in_stride, typename F::T* __restrict__ out, uint64_t out_stride,
-            const typename F::T* __restrict__ wtab, int a, int b, int logB, int logR) {
+MS_HD void tile_round(const NttTile<F>& g, typename F::T* S, const typename F::T* src, typename F::T* dst, uint32_t tile,
+                      int round, int u, int G, uint32_t tid, uint32_t nthreads) {
+    const bool first = round == 0, last = round == tile_rounds(g.a) - 1 || g.a == 0;
+    const uint32_t nslots = 1u << (g.a - G + g.beta);
+    for (uint32_t s = tid; s < nslots; s += nthreads) {
+        switch (G) {
+            case 4: tile_slot<F, 4>(g, S, src, dst, tile, s, u, first, last); break;
+            case 3: tile_slot<F, 3>(g, S, src, dst, tile, s, u, first, last); break;
+            case 2: tile_slot<F, 2>(g, S, src, dst, tile, s, u, first, last); break;
+            case 1: tile_slot<F, 1>(g, S, src, dst, tile, s, u, first, last); break;
+            default: tile_slot<F, 0>(g, S, src, dst, tile, s, u, true, true); break;
+        }
+    }
+}
+
+// block -> (column, tile): 8 neighbouring tiles of every column run in the same wave, so the 32-byte
+// sectors pass 1 touches (8 of 32 bytes per tile) and the ft rows are shared through L2
+template <class F>
+MS_HD void tile_of_block(const NttTile<F>& g, uint32_t bid, uint32_t* col, uint32_t* tile) {
+    const uint32_t grp = g.tiles < 8 ? g.tiles : 8;
+    const uint32_t tl = bid % grp, rest = bid / grp;
+    *col = rest % g.cols;
+    *tile = (rest / g.cols) * grp + tl;
+}
+
+template <class F>
+__global__ void __launch_bounds__(NTT_THREADS, 2)
+k_ntt_tile(const NttTile<F> g) {
     using T = typename F::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);
-    const int logRB = logR + logB;
-    const uint64_t n1 = 1ULL << b, n2 = 1ULL << a;
-    const uint64_t k2_0 = (uint64_t)blockIdx.y << logR;
-    const T* src = in + (uint64_t)blockIdx.x * in_stride + ((n1 * k2_0) << logB);
-    T* dst = out + (uint64_t)blockIdx.x * out_stride;
-    const uint32_t tile = (uint32_t)(n1 << logRB);
-    const uint32_t Bm = (1u << logB) - 1, RBm = (1u << logRB) - 1;
-    for (uint32_t s = threadIdx.x; s < tile; s += blockDim.x) {
-        uint32_t beta = s & RBm, P = s >> logRB;
-        uint32_t r2 = beta >> logB, j = beta & Bm;
-        uint64_t m1 = brev_bits(P, b);
-        S[s] = src[(((uint64_t)r2 * n1 + m1) << logB) + j];
+    uint32_t col, tile;
+    tile_of_block<F>(g, blockIdx.x, &col, &tile);
+    const T* src = g.src + (uint64_t)col * g.src_stride;
+    T* dst = g.dst + (uint64_t)col * g.dst_stride;
+    const int nr = tile_rounds(g.a);
+    if (nr == 0) {
+        tile_round<F>(g, S, src, dst, tile, 0, 0, 0, threadIdx.x, blockDim.x);
+        return;
     }
-    tile_dit<F>(S, b, logRB, wtab, 0u, 0u);
-    for (uint32_t s = threadIdx.x; s < tile; s += blockDim.x) {
-        uint32_t beta = s & RBm;
-        uint64_t k1 = s >> logRB;
-        dst[((k1 * n2 + k2_0) << logB) + beta] = S[s];
+    int u = 0;
+    for (int r = 0; r < nr; r++) {
+        const int G = tile_round_size(g.a, r);
+        if (r) __syncthreads();
+        tile_round<F>(g, S, src, dst, tile, r, u, G, threadIdx.x, blockDim.x);
+        u += G;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Specialised tile kernel: tile shape (A points, BETA batch bits) fixed at compile time, so the
+// round structure is unrolled and every per-element index is base + constant (global: base +
+// constant * stride).  Same algorithm and the same result as k_ntt_tile; the generic kernel stays
+// as the path for unusual shapes.
+// ------------------------------------------------------------------------------------------------
+template <int A>
+struct Rounds {
+    static constexpr int NR = (A + NTT_MAXG - 1) / NTT_MAXG;
+    static constexpr int size(int r) { return A / NR + (r < A % NR ? 1 : 0); }
+    static constexpr int start(int r) {
+        int u = 0;
+        for (int i = 0; i < r; i++) u += size(i);
+        return u;
+    }
+};
+constexpr uint32_t cbrev(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+template <class F, int A, int BETA>
+struct FixedSwz {
+    static constexpr int G0 = Rounds<A>::size(0);
+    static constexpr int BANKBITS = sizeof(typename F::T) == 8 ? 4 : 5;
+    static constexpr int K0 = BANKBITS > BETA ? BANKBITS - BETA : 0;
+    static constexpr int K1 = K0 < G0 ? K0 : G0;
+    static constexpr int K = K1 < A - G0 ? K1 : (A - G0 > 0 ? A - G0 : 0);  // swizzle bits
+    static constexpr uint32_t MASK = (1u << K) - 1;
+};
+
+template <class F, int A, int BETA, int R, int THREADS>
+MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::T* __restrict__ src,
+                       typename F::T* __restrict__ dst, uint32_t tile, uint32_t tid) {
+    using T = typename F::T;
+    using Ar = Fast<F>;
+    using SW = FixedSwz<F, A, BETA>;
+    constexpr int G = Rounds<A>::size(R), U = Rounds<A>::start(R), E = 1 << G;
+    constexpr bool FIRST = R == 0, LAST = R == Rounds<A>::NR - 1;
+    constexpr uint32_t NSLOTS = 1u << (A - G + BETA);
+    const int logR = BETA - g.logB;  // pass 1: log2 R1, pass 2: log2 R2
+#pragma unroll 1
+    for (uint32_t s = tid; s < NSLOTS; s += THREADS) {
+        const uint32_t b = s & ((1u << BETA) - 1), t = s >> BETA;
+        const uint32_t lo = t & ((1u << U) - 1), hi = t >> U;
+        const uint32_t P0 = lo | (hi << (U + G));
+        const T* __restrict__ twj = g.tw + (size_t)(b & g.jmask) * g.jstride + lo;
+        T w[E];
+#pragma unroll
+        for (int st = 0; st < G; st++)
+#pragma unroll
+            for (int r = 0; r < (1 << st); r++) w[(1 << st) + r] = MS_LDG(&twj[(1u << (U + st)) + ((uint32_t)r << U)]);
+        T v[E];
+        if (FIRST) {
+            // element r sits at position P0 + r whose bit reversal is brev(P0) | brev_G(r) << (A - G)
+            const uint32_t m0 = brev_bits(P0, A);
+            const T* p;
+            uint32_t stride;  // elements between brev_G(r) = 1 and 2
+            if (g.mode == 0) {
+                p = src + ((uint64_t)tile << logR) + (b >> g.logB) + ((uint64_t)m0 << g.bq);
+                stride = 1u << (A - G + g.bq);
+            } else {
+                const uint64_t k2 = ((uint64_t)tile << logR) + (b >> g.logB);
+                const uint32_t j = b & ((1u << g.logB) - 1);
+                p = src + ((((((uint64_t)m0 >> g.logR1) << g.a1) + k2) << g.beta1) | ((m0 & ((1u << g.logR1) - 1)) << g.logB)) + j;
+                stride = 1u << (A - G - g.logR1 + g.a1 + g.beta1);
+            }
+#pragma unroll
+            for (int r = 0; r < E; r++) v[r] = p[(uint64_t)cbrev(r, G) * stride];
+        } else {
+            const uint32_t Pb = P0 ^ ((P0 >> SW::G0) & SW::MASK);
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const uint32_t cr = (((uint32_t)r << U) >> SW::G0) & SW::MASK;
+                v[r] = S[((((Pb ^ cr) << BETA) | b)) + ((uint32_t)r << (U + BETA))];
+            }
+        }
+#pragma unroll
+        for (int st = 0; st < G; st++) {
+            const int h = 1 << st;
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                if (r & h) continue;
+                T x = Ar::mul(v[r | h], w[h + (r & (h - 1))]);
+                T y = v[r];
+                v[r] = Ar::add(y, x);
+                v[r | h] = Ar::sub(y, x);
+            }
+        }
+        if (LAST) {
+            // positions P0 + (r << U) with U + G == A: consecutive lanes hold consecutive (b, lo)
+            uint64_t o;
+            uint32_t stride;
+            if (g.mode == 0) {
+                o = ((((uint64_t)tile << A) + P0) << BETA) | b;
+                stride = 1u << (U + BETA);
+            } else {
+                const uint64_t k2 = ((uint64_t)tile << logR) + (b >> g.logB);
+                const uint32_t j = b & ((1u << g.logB) - 1);
+                o = ((((uint64_t)P0 << g.a1) + k2) << g.logB) | j;
+                stride = 1u << (U + g.a1 + g.logB);
+            }
+            T* q = dst + o;
+            if (g.ft) {
+                const T* __restrict__ f = g.ft + o;
+#pragma unroll
+                for (int r = 0; r < E; r++) q[(uint64_t)r * stride] = Ar::mul(v[r], MS_LDG(&f[(uint64_t)r * stride]));
+            } else if (g.has_scale) {
+#pragma unroll
+                for (int r = 0; r < E; r++) q[(uint64_t)r * stride] = Ar::mul(v[r], g.scale);
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; r++) q[(uint64_t)r * stride] = Ar::canon(v[r]);
+            }
+        } else if (FIRST) {
+            // U == 0: the swizzle term depends on hi only and permutes the slot's E positions
+            const uint32_t m = (P0 >> SW::G0) & SW::MASK;
+#pragma unroll
+            for (int r = 0; r < E; r++) S[((P0 | ((uint32_t)r ^ m)) << BETA) | b] = v[r];
+        } else {
+            const uint32_t Pb = P0 ^ ((P0 >> SW::G0) & SW::MASK);
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const uint32_t cr = (((uint32_t)r << U) >> SW::G0) & SW::MASK;
+                S[(((Pb ^ cr) << BETA) | b) + ((uint32_t)r << (U + BETA))] = v[r];
+            }
+        }
+    }
+}
+
+template <class F, int A, int BETA, int R, int THREADS>
+__device__ __forceinline__ void fixed_rounds_from(const NttTile<F>& g, typename F::T* S, const typename F::T* src,
+                                                  typename F::T* dst, uint32_t tile) {
+    if constexpr (R < Rounds<A>::NR) {
+        if (R) __syncthreads();
+        fixed_round<F, A, BETA, R, THREADS>(g, S, src, dst, tile, threadIdx.x);
+        fixed_rounds_from<F, A, BETA, R + 1, THREADS>(g, S, src, dst, tile);
+    }
+}
+
+template <class F, int A, int BETA, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_ntt_fixed(const NttTile<F> g) {
+    using T = typename F::T;
+    static_assert(Rounds<A>::NR >= 2, "fixed tiles have at least two rounds");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* S = reinterpret_cast<T*>(smem_raw);
+    uint32_t col, tile;
+    tile_of_block<F>(g, blockIdx.x, &col, &tile);
+    fixed_rounds_from<F, A, BETA, 0, THREADS>(g, S, g.src + (uint64_t)col * g.src_stride, g.dst + (uint64_t)col * g.dst_stride, tile);
 }
 
 template <class F>
@@ -199,7 +580,10 @@ __global__ void k_transpose(const typename F::T* __restrict__ in, typename F::T*
     }
 }
 
-// -------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+#ifndef MS_NTT_NO_HOST
 template <class F>
 int ensure_wtab(Ctx* c, int inverse) {
     using T = typename F::T;
@@ -221,9 +605,11 @@ int ensure_wtab(Ctx* c, int inverse) {
     c->wtab[inverse] = w;
     return MS_OK;
 }
+#endif
 
 struct NttPlan {
-    int a, b, logR1, logR2;
+    int a, b;        // N = 2^(a+b): pass 1 transforms 2^a points (stride 2^b), pass 2 2^b points
+    int logR1, logR2;  // extra batch per tile: consecutive m1 (pass 1) / consecutive k2 (pass 2)
 };
 inline bool ntt_plan(int logN, int logB, NttPlan* p) {
     if (logN + logB <= NTT_LOG_TILE_PREF) {
@@ -231,7 +617,12 @@ inline bool ntt_plan(int logN, int logB, NttPlan* p) {
         return true;
     }
     int a = (logN + 1) / 2, b = logN - a;
-    if (a + logB > NTT_LOG_TILE_MAX) return false;
+    if (a + logB > NTT_LOG_TILE_MAX) {  // large blowup: shift stages into the second pass
+        a = NTT_LOG_TILE_MAX - logB;
+        if (a < 1) return false;
+        b = logN - a;
+    }
+    if (b + logB > NTT_LOG_TILE_MAX) return false;
     int r1 = NTT_LOG_TILE_PREF - a - logB;
     if (r1 < 0) r1 = 0;
     if (r1 > b) r1 = b;
@@ -242,8 +633,47 @@ inline bool ntt_plan(int logN, int logB, NttPlan* p) {
     return true;
 }
 
-// See the header comment.  `d_tmp` (cols * (N<<logB) elements) is only needed for two-pass sizes;
-// pass nullptr to have it allocated from the stream-ordered pool.
+#ifndef MS_NTT_NO_HOST
+template <class F, int A, int BETA>
+int launch_fixed(Ctx* c, const NttTile<F>& g, const char* name) {
+    using T = typename F::T;
+    constexpr size_t smem = sizeof(T) << (A + BETA);
+    constexpr bool big = smem > 100 * 1024;  // one CTA per SM: give it 512 threads
+    constexpr int threads = big ? 512 : 256;
+    auto kern = k_ntt_fixed<F, A, BETA, threads, big ? 1 : 2>;
+    MS_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(c, name);
+    kern<<<g.cols * g.tiles, threads, smem, c->stream>>>(g);
+    prof_end(c);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+
+// tile shapes with a compile-time specialisation
+#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2) X(11, 3)
+
+template <class F>
+int launch_tile(Ctx* c, const NttTile<F>& g, const char* name) {
+    using T = typename F::T;
+    if (g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0)) {
+#define X(A_, B_) if (g.a == A_ && g.beta == B_) return launch_fixed<F, A_, B_>(c, g, name);
+        MS_NTT_FIXED_SHAPES(X)
+#undef X
+    }
+    const size_t smem = tile_rounds(g.a) > 1 ? (sizeof(T) << (g.a + g.beta)) : 0;
+    if (smem > 48 * 1024)
+        MS_CUDA(c, cudaFuncSetAttribute(k_ntt_tile<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t slots = 1ULL << (g.a + g.beta - (g.a ? tile_round_size(g.a, 0) : 0));
+    unsigned threads = NTT_THREADS;
+    while (threads > 32 && threads / 2 >= slots) threads /= 2;
+    prof_begin(c, name);
+    k_ntt_tile<F><<<g.cols * g.tiles, threads, smem, c->stream>>>(g);
+    prof_end(c);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+
+// See the header comment.  d_in and d_out must not alias.
 template <class F>
 int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t cols, int logN, int logB,
               typename F::T shift, bool inverse, typename F::T* d_out, uint64_t out_stride) {
@@ -251,6 +681,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     if (cols == 0) return MS_OK;
     if (logN + logB > F::TWO_ADICITY) return fail(c, MS_ERR_BAD_SHAPE, "domain 2^%d exceeds the field's two-adicity", logN + logB);
     if (inverse && logB != 0) return fail(c, MS_ERR_UNSUPPORTED, "inverse transform with blowup");
+    if (cols >= (1ULL << 20)) return fail(c, MS_ERR_UNSUPPORTED, "too many columns");
     NttPlan pl;
     if (!ntt_plan(logN, logB, &pl)) return fail(c, MS_ERR_UNSUPPORTED, "transform 2^%d x blowup 2^%d too large", logN, logB);
     MS_TRY(ensure_wtab<F>(c, inverse ? 1 : 0));
@@ -259,65 +690,95 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     const uint64_t N = 1ULL << logN;
     T wN = root_of_unity<F>(logN);
     if (inverse) wN = finv<F>(wN);
-    T scale = inverse ? finv<F>((T)(N % (uint64_t)F::P)) : (T)1;
-    T wL = root_of_unity<F>(logN + logB);
+    const T scale = inverse ? finv<F>((T)(N % (uint64_t)F::P)) : (T)1;
+    const T wL = root_of_unity<F>(logN + logB);
+    const bool two = pl.b > 0;
     // host-side per-coset constants
-    std::vector<T> hbuf((size_t)B * (pl.a ? pl.a : 1) + B);
+    const int na = pl.a ? pl.a : 1;
+    std::vector<T> hbuf((size_t)B * na + B);
     T* sbase = hbuf.data();
-    T* shifts = hbuf.data() + (size_t)B * (pl.a ? pl.a : 1);
+    T* shifts = hbuf.data() + (size_t)B * na;
     T sj = shift;
+    bool plain = true;  // every coset's stage factors are 1: use the plain table
     for (int j = 0; j < B; j++) {
         shifts[j] = sj;
-        for (int u = 0; u < pl.a; u++) sbase[j * pl.a + u] = fpow<F>(sj, N >> (u + 1));
+        for (int u = 0; u < pl.a; u++) {
+            sbase[j * na + u] = fpow<F>(sj, N >> (u + 1));
+            plain = plain && sbase[j * na + u] == 1;
+        }
         sj = F::mul(sj, wL);
     }
     Scratch consts(c), t1(c), ft(c), tmp(c);
-    MS_TRY(consts.alloc(hbuf.size() * sizeof(T)));
-    MS_CUDA(c, cudaMemcpyAsync(consts.p, hbuf.data(), hbuf.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-    // the H2D source must stay alive until the copy ran (pageable memory: the call is synchronous
-    // with respect to the host buffer for pageable sources, so this is safe)
-    const T* d_sbase = consts.as<T>();
-    const T* d_shifts = d_sbase + (size_t)B * (pl.a ? pl.a : 1);
-    MS_TRY(t1.alloc(((size_t)B << pl.a) * sizeof(T)));
-    if (pl.a > 0) {
+    const T* d_tw1 = wtab;
+    if (!plain) {
+        MS_TRY(consts.alloc(hbuf.size() * sizeof(T)));
+        MS_CUDA(c, cudaMemcpyAsync(consts.p, hbuf.data(), hbuf.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        MS_TRY(t1.alloc(((size_t)B << pl.a) * sizeof(T)));
         int n = B << pl.a;
         prof_begin(c, "k_build_t1");
-        k_build_t1<F><<<(n + 255) / 256, 256, 0, c->stream>>>(t1.as<T>(), wtab, d_sbase, pl.a, B);
+        k_build_t1<F><<<(n + 255) / 256, 256, 0, c->stream>>>(t1.as<T>(), wtab, consts.as<T>(), pl.a, B);
         prof_end(c);
         MS_LAUNCH_CHECK(c);
+        d_tw1 = t1.as<T>();
     }
-    const bool two = pl.b > 0;
+    const bool inplace = two && pl.logR1 == 0 && tile_rounds(pl.b) >= 2;
     if (two) {
+        if (plain) {  // the shifts are still needed by k_build_ft
+            MS_TRY(consts.alloc(hbuf.size() * sizeof(T)));
+            MS_CUDA(c, cudaMemcpyAsync(consts.p, hbuf.data(), hbuf.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        }
+        const T* d_shifts = consts.as<T>() + (size_t)B * na;
         MS_TRY(ft.alloc(((size_t)N << logB) * sizeof(T)));
         int chunk_log = pl.a < 6 ? pl.a : 6;
         uint64_t threads = (((uint64_t)1 << pl.b) << logB) * ((1ULL << pl.a) >> chunk_log);
         prof_begin(c, "k_build_ft");
-        k_build_ft<F><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(ft.as<T>(), d_shifts, wN, scale, pl.a, pl.b, logB, chunk_log);
+        k_build_ft<F><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(ft.as<T>(), d_shifts, wN, scale, pl.a, pl.b, logB,
+                                                                               pl.logR1, chunk_log);
         prof_end(c);
         MS_LAUNCH_CHECK(c);
-        MS_TRY(tmp.alloc(cols * ((size_t)N << logB) * sizeof(T)));
+        if (!inplace) MS_TRY(tmp.alloc(cols * ((size_t)N << logB) * sizeof(T)));
     }
-    {
-        size_t smem = ((size_t)sizeof(T) << pl.a) << (pl.logR1 + logB);
-        MS_CUDA(c, cudaFuncSetAttribute(k_lde_pass1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)cols, (unsigned)((1ULL << pl.b) >> pl.logR1));
-        T* o = two ? tmp.as<T>() : d_out;
-        uint64_t os = two ? ((uint64_t)N << logB) : out_stride;
-        prof_begin(c, "k_lde_pass1");
-        k_lde_pass1<F><<<grid, NTT_THREADS, smem, c->stream>>>(d_in, in_stride, o, os, t1.as<T>(), two ? ft.as<T>() : nullptr,
-                                                               pl.a, pl.b, logB, pl.logR1, scale);
-        prof_end(c);
-        MS_LAUNCH_CHECK(c);
-    }
+    NttTile<F> g1{};
+    g1.src = d_in;
+    g1.src_stride = in_stride;
+    g1.dst = two ? (inplace ? d_out : tmp.as<T>()) : d_out;
+    g1.dst_stride = two ? (inplace ? out_stride : ((uint64_t)N << logB)) : out_stride;
+    g1.tw = d_tw1;
+    g1.ft = two ? ft.as<T>() : nullptr;
+    g1.scale = Fast<F>::to_tw(scale);
+    g1.has_scale = (!two && scale != 1) ? 1 : 0;
+    g1.a = pl.a;
+    g1.beta = pl.logR1 + logB;
+    g1.logB = logB;
+    g1.jmask = plain ? 0u : (uint32_t)(B - 1);
+    g1.jstride = plain ? 0u : (1u << pl.a);
+    g1.mode = 0;
+    g1.bq = pl.b;
+    g1.tiles = (uint32_t)((1ULL << pl.b) >> pl.logR1);
+    g1.cols = (uint32_t)cols;
+    MS_TRY(launch_tile<F>(c, g1, "k_ntt_tile/pass1"));
     if (two) {
-        size_t smem = ((size_t)sizeof(T) << pl.b) << (pl.logR2 + logB);
-        MS_CUDA(c, cudaFuncSetAttribute(k_lde_pass2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)cols, (unsigned)((1ULL << pl.a) >> pl.logR2));
-        prof_begin(c, "k_lde_pass2");
-        k_lde_pass2<F><<<grid, NTT_THREADS, smem, c->stream>>>(tmp.as<T>(), (uint64_t)N << logB, d_out, out_stride, wtab,
-                                                               pl.a, pl.b, logB, pl.logR2);
-        prof_end(c);
-        MS_LAUNCH_CHECK(c);
+        NttTile<F> g2{};
+        g2.src = g1.dst;
+        g2.src_stride = g1.dst_stride;
+        g2.dst = d_out;
+        g2.dst_stride = out_stride;
+        g2.tw = wtab;
+        g2.ft = nullptr;
+        g2.scale = 0;
+        g2.has_scale = 0;
+        g2.a = pl.b;
+        g2.beta = pl.logR2 + logB;
+        g2.logB = logB;
+        g2.jmask = 0;
+        g2.jstride = 0;
+        g2.mode = 1;
+        g2.a1 = pl.a;
+        g2.beta1 = g1.beta;
+        g2.logR1 = pl.logR1;
+        g2.tiles = (uint32_t)((1ULL << pl.a) >> pl.logR2);
+        g2.cols = (uint32_t)cols;
+        MS_TRY(launch_tile<F>(c, g2, "k_ntt_tile/pass2"));
     }
     return MS_OK;
 }
@@ -330,5 +791,6 @@ int transpose(Ctx* c, const typename F::T* d_in, typename F::T* d_out, uint64_t 
     MS_LAUNCH_CHECK(c);
     return MS_OK;
 }
+#endif  // MS_NTT_NO_HOST
 
 }  // namespace ms

@@ -1,0 +1,191 @@
+// Host emulation of k_ntt_tile (tests/test_ntt_emulation.py): the per-thread round body of
+// csrc/ntt.cuh is __host__ __device__, so the index maps, round structure, swizzle and twiddle
+// tables can be checked on a CPU-only box against a naive evaluation.  Test infrastructure only.
+#define MS_NTT_NO_HOST
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../ministark_b200/csrc/ntt.cuh"
+using namespace ms;
+
+template <class F>
+static void run_tiles(const NttTile<F>& g, unsigned threads) {
+    using T = typename F::T;
+    std::vector<T> S((size_t)1 << (g.a + g.beta));
+    for (uint32_t bid = 0; bid < g.cols * g.tiles; bid++) {
+        uint32_t col, tile;
+        tile_of_block<F>(g, bid, &col, &tile);
+        const T* src = g.src + (uint64_t)col * g.src_stride;
+        T* dst = g.dst + (uint64_t)col * g.dst_stride;
+        int nr = tile_rounds(g.a);
+        if (nr == 0) {
+            for (unsigned t = 0; t < threads; t++) tile_round<F>(g, S.data(), src, dst, tile, 0, 0, 0, t, threads);
+            continue;
+        }
+        int u = 0;
+        for (int r = 0; r < nr; r++) {
+            int G = tile_round_size(g.a, r);
+            for (unsigned t = 0; t < threads; t++) tile_round<F>(g, S.data(), src, dst, tile, r, u, G, t, threads);
+            u += G;
+        }
+    }
+}
+
+template <class F, int A, int BETA, int R>
+static void emu_fixed_rounds(const NttTile<F>& g, typename F::T* S, const typename F::T* src, typename F::T* dst, uint32_t tile) {
+    if constexpr (R < Rounds<A>::NR) {
+        for (uint32_t t = 0; t < 256; t++) fixed_round<F, A, BETA, R, 256>(g, S, src, dst, tile, t);
+        emu_fixed_rounds<F, A, BETA, R + 1>(g, S, src, dst, tile);
+    }
+}
+template <class F, int A, int BETA>
+static void run_fixed(const NttTile<F>& g) {
+    using T = typename F::T;
+    std::vector<T> S((size_t)1 << (A + BETA));
+    for (uint32_t bid = 0; bid < g.cols * g.tiles; bid++) {
+        uint32_t col, tile;
+        tile_of_block<F>(g, bid, &col, &tile);
+        emu_fixed_rounds<F, A, BETA, 0>(g, S.data(), g.src + (uint64_t)col * g.src_stride, g.dst + (uint64_t)col * g.dst_stride, tile);
+    }
+}
+static int g_fixed_used = 0;
+template <class F>
+static void run_any(const NttTile<F>& g) {
+    if (g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0)) {
+#define X(A_, B_) if (g.a == A_ && g.beta == B_) { g_fixed_used++; return run_fixed<F, A_, B_>(g); }
+        X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2) X(11, 3) X(5, 2) X(6, 0) X(7, 3)
+#undef X
+    }
+    run_tiles<F>(g, 64);
+}
+
+// mirrors lde_batch (csrc/ntt.cuh) with host tables
+template <class F>
+static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, uint64_t cols, int logN, int logB,
+                                          typename F::T shift, bool inverse, int force_a) {
+    using T = typename F::T;
+    NttPlan pl;
+    if (!ntt_plan(logN, logB, &pl)) { printf("plan failed\n"); exit(2); }
+    if (force_a >= 0) {  // exercise two-pass geometry on small sizes
+        pl.a = force_a; pl.b = logN - force_a;
+        pl.logR1 = 0; pl.logR2 = 0;
+        if (logB == 0 && pl.b >= 2) pl.logR1 = 2;
+        if (logB == 0 && pl.a >= 1) pl.logR2 = 1;
+    }
+    const int B = 1 << logB;
+    const uint64_t N = 1ULL << logN;
+    std::vector<T> wtab((size_t)1 << NTT_MAXLOG, 0);
+    for (int u = 0; u < NTT_MAXLOG; u++) {
+        T g = (u + 1 <= F::TWO_ADICITY) ? root_of_unity<F>(u + 1) : (T)1;
+        if (inverse) g = finv<F>(g);
+        for (int q = 0; q < (1 << u); q++) wtab[(1 << u) + q] = Fast<F>::to_tw(fpow<F>(g, q));
+    }
+    T wN = root_of_unity<F>(logN);
+    if (inverse) wN = finv<F>(wN);
+    const T scale = inverse ? finv<F>((T)(N % (uint64_t)F::P)) : (T)1;
+    const T wL = root_of_unity<F>(logN + logB);
+    const bool two = pl.b > 0;
+    std::vector<T> shifts(B), t1((size_t)B << pl.a, 0);
+    T sj = shift;
+    for (int j = 0; j < B; j++) {
+        shifts[j] = sj;
+        for (int u = 0; u < pl.a; u++) {
+            T sb = fpow<F>(sj, N >> (u + 1));
+            for (int q = 0; q < (1 << u); q++) t1[((size_t)j << pl.a) + (1 << u) + q] = F::mul(sb, wtab[(1 << u) + q]);
+        }
+        sj = F::mul(sj, wL);
+    }
+    std::vector<T> ft, tmp, out(cols * (N << logB), 0);
+    const bool inplace = two && pl.logR1 == 0 && tile_rounds(pl.b) >= 2;
+    if (two) {
+        ft.resize(N << logB);
+        const int beta = pl.logR1 + logB;
+        for (uint64_t m1 = 0; m1 < (1ULL << pl.b); m1++)
+            for (int j = 0; j < B; j++)
+                for (uint64_t k2 = 0; k2 < (1ULL << pl.a); k2++) {
+                    uint64_t tile = m1 >> pl.logR1, rr = m1 & ((1u << pl.logR1) - 1);
+                    T v = F::mul(F::mul(scale, fpow<F>(shifts[j], m1)), fpow<F>(wN, m1 * k2));
+                    ft[((((tile << pl.a) + k2) << beta) | (rr << logB)) + j] = Fast<F>::to_tw(v);
+                }
+        if (!inplace) tmp.resize(cols * (N << logB));
+    }
+    NttTile<F> g1{};
+    g1.src = in.data(); g1.src_stride = N;
+    g1.dst = two ? (inplace ? out.data() : tmp.data()) : out.data();
+    g1.dst_stride = N << logB;
+    g1.tw = t1.data(); g1.ft = two ? ft.data() : nullptr;
+    g1.scale = Fast<F>::to_tw(scale); g1.has_scale = (!two && scale != 1) ? 1 : 0;
+    g1.a = pl.a; g1.beta = pl.logR1 + logB; g1.logB = logB;
+    g1.jmask = B - 1; g1.jstride = 1u << pl.a; g1.mode = 0; g1.bq = pl.b;
+    g1.tiles = (uint32_t)((1ULL << pl.b) >> pl.logR1); g1.cols = (uint32_t)cols;
+    run_any<F>(g1);
+    if (two) {
+        NttTile<F> g2{};
+        g2.src = g1.dst; g2.src_stride = g1.dst_stride; g2.dst = out.data(); g2.dst_stride = N << logB;
+        g2.tw = wtab.data(); g2.a = pl.b; g2.beta = pl.logR2 + logB; g2.logB = logB; g2.mode = 1;
+        g2.a1 = pl.a; g2.beta1 = g1.beta; g2.logR1 = pl.logR1;
+        g2.tiles = (uint32_t)((1ULL << pl.a) >> pl.logR2); g2.cols = (uint32_t)cols;
+        run_any<F>(g2);
+    }
+    return out;
+}
+
+template <class F>
+static int check(int logN, int logB, bool inverse, int force_a, uint64_t cols) {
+    using T = typename F::T;
+    const uint64_t N = 1ULL << logN, L = N << logB;
+    std::vector<T> in(cols * N);
+    uint64_t s = 0x9E3779B97F4A7C15ULL * (logN * 131 + logB * 7 + inverse + 1);
+    for (auto& v : in) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = (T)(s % (uint64_t)F::P); }
+    T shift = inverse ? (T)1 : (T)(0x1234567ULL % (uint64_t)F::P);
+    auto out = emu_lde<F>(in, cols, logN, logB, shift, inverse, force_a);
+    // naive: out[c][i] = sum in[c][m] (shift w_L^i)^m  (inverse: w_N^-1, scaled 1/N)
+    T wL = root_of_unity<F>(logN + logB);
+    if (inverse) wL = finv<F>(wL);
+    T scale = inverse ? finv<F>((T)(N % (uint64_t)F::P)) : (T)1;
+    int bad = 0;
+    for (uint64_t c = 0; c < cols; c++)
+        for (uint64_t i = 0; i < L; i += (L > 256 ? 37 : 1)) {
+            T x = F::mul(shift, fpow<F>(wL, i)), acc = 0;
+            for (uint64_t m = N; m-- > 0;) acc = F::add(F::mul(acc, x), in[c * N + m]);
+            acc = F::mul(acc, scale);
+            if (acc != out[c * L + i]) bad++;
+        }
+    printf("field %d logN %d logB %d inv %d force_a %d: %s\n", F::ID, logN, logB, (int)inverse, force_a, bad ? "MISMATCH" : "ok");
+    return bad;
+}
+
+int main() {
+    int bad = 0;
+    for (int logN = 0; logN <= 11; logN++)
+        for (int logB = 0; logB <= 3; logB++) {
+            bad += check<GL>(logN, logB, false, -1, 2);
+            if (logB == 0) bad += check<GL>(logN, 0, true, -1, 2);
+        }
+    for (int logN = 4; logN <= 10; logN += 3)
+        for (int fa = 1; fa < logN; fa += 2)
+            for (int logB = 0; logB <= 2; logB += 2) {
+                bad += check<GL>(logN, logB, false, fa, 3);
+                bad += check<BB>(logN, logB, false, fa, 3);
+                if (logB == 0) bad += check<GL>(logN, 0, true, fa, 3);
+            }
+    for (int logN = 0; logN <= 9; logN += 3) bad += check<BB>(logN, 1, false, -1, 2) + check<BB>(logN, 0, true, -1, 1);
+    bad += check<GL>(11, 2, false, -1, 1);   // single pass, fixed (11,2)
+    bad += check<BB>(11, 2, false, -1, 1);
+    bad += check<GL>(10, 3, false, -1, 1);   // fixed (10,3)
+    bad += check<GL>(16, 2, false, -1, 1);   // two-pass (8,5)/(8,5)
+    bad += check<BB>(16, 2, false, -1, 1);
+    bad += check<GL>(17, 2, false, -1, 1);   // (9,4) + (8,5)
+    bad += check<GL>(16, 0, true, -1, 2);    // iNTT two-pass with R1 = R2 = 32
+    bad += check<GL>(18, 0, true, -1, 1);
+    bad += check<BB>(18, 0, true, -1, 1);
+    bad += check<GL>(7, 2, false, 5, 1);     // (5,2) pass 1 fixed
+    bad += check<GL>(12, 0, false, 6, 1);    // (6,0): 4-bit swizzle
+    bad += check<BB>(12, 0, false, 6, 1);
+    bad += check<GL>(10, 3, false, 7, 1);    // (7,3)
+    bad += check<GL>(12, 2, false, -1, 1);   // real two-pass plan
+    bad += check<GL>(14, 0, true, -1, 1);
+    printf("fixed-shape tiles used: %d\n", g_fixed_used);
+    printf(bad ? "FAILED\n" : "ALL OK\n");
+    return bad ? 1 : 0;
+}
