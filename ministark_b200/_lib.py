@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libministark.so")
+LIB_PATH = os.environ.get("MINISTARK_LIB") or os.path.join(HERE, "libministark.so")  # env: A/B builds
 
 MS_OK = 0
 ERR_NAMES = {

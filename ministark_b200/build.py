@@ -30,18 +30,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in sources() + [hdr])
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: list[str] | None = None) -> str:
+    """out/defines: experimental A/B builds (MINISTARK_LIB=<out> selects one at run time)"""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "ministark.cu")]
+    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in (defines or [])]
+           + ["-o", out or LIB, os.path.join(CSRC, "ministark.cu")])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libministark.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

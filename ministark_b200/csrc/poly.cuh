@@ -73,6 +73,12 @@ int mix(Ctx* c, const typename F::T* d_coef, uint64_t stride, uint64_t n, uint64
 
 // ------------------------------------------------------------------------------------------ evaluation
 // Sequence element i of polynomial `poly`: coordinate d at coef[(poly*CD + d)*stride + off + i*step].
+// f(z) = sum_i c_i z^i is computed without a dependency chain: block b, thread t, k < EV_SEG owns
+// i = b*EV_BLOCK + k*EV_THREADS + t (coalesced), so
+//   f(z) = sum_b Zb[b] * sum_t zt[t] * sum_k c_i * z256[k],   zt[t] = z^t, z256[k] = z^(256k), Zb[b] = z^(2048b)
+// with the three power tables built once per call (k_eval_powers).  For base-field coefficients
+// (trace / constraint polynomials, src/starks.rs:140-151) the inner products are base x extension,
+// i.e. D base multiplications each; one coefficient load serves all Q points.
 template <class F, int CD>
 __device__ __forceinline__ Ext<F> load_coef(const typename F::T* __restrict__ coef, uint64_t stride, uint64_t poly, uint64_t idx) {
     Ext<F> r = ext_zero<F>();
@@ -81,64 +87,89 @@ __device__ __forceinline__ Ext<F> load_coef(const typename F::T* __restrict__ co
     return r;
 }
 
-// block-level value sum_t v_t * z^(seg*t) via a tree; result valid in thread 0
+// tables for Q points: [q][0..EV_THREADS) z^t | [q][EV_THREADS..+EV_SEG) z^(256 k) | [q][..+nblk) z^(2048 b)
 template <class F>
-__device__ __forceinline__ Ext<F> block_tree(Ext<F> v, Ext<F> zseg, Ext<F>* sm) {
-    const int t = threadIdx.x;
-    sm[t] = v;
-    Ext<F> pw = zseg;
-    for (int ofs = 1; ofs < EV_THREADS; ofs <<= 1) {
-        __syncthreads();
-        if ((t & (2 * ofs - 1)) == 0) sm[t] = ext_add(sm[t], ext_mul(sm[t + ofs], pw));
-        pw = ext_mul(pw, pw);
-    }
-    __syncthreads();
-    Ext<F> r = sm[0];
-    __syncthreads();
-    return r;
+__global__ void k_eval_powers(const Ext<F>* __restrict__ z, int Q, uint64_t nblk, Ext<F>* __restrict__ tab) {
+    const uint64_t per_q = EV_THREADS + EV_SEG + nblk;
+    uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_q * Q) return;
+    const int q = (int)(gid / per_q);
+    const uint64_t i = gid % per_q;
+    Ext<F> v;
+    if (i < EV_THREADS) v = ext_pow<F>(z[q], i);
+    else if (i < EV_THREADS + EV_SEG) v = ext_pow<F>(z[q], (uint64_t)EV_THREADS * (i - EV_THREADS));
+    else v = ext_pow<F>(ext_pow<F>(z[q], EV_BLOCK), i - EV_THREADS - EV_SEG);
+    tab[gid] = v;
 }
 
 template <class F, int CD>
+__device__ __forceinline__ Ext<F> coef_times(const Ext<F>& c, const Ext<F>& p) {
+    if (CD == 1) return ext_mul_base(p, c.c[0]);
+    return ext_mul(c, p);
+}
+
+template <class F, int CD, int QMAX>
 __global__ void __launch_bounds__(EV_THREADS)
 k_eval_partial(const typename F::T* __restrict__ coef, uint64_t stride, uint64_t off, uint64_t step, uint64_t n,
-               const Ext<F>* __restrict__ z, int Q, Ext<F>* __restrict__ partial) {
-    __shared__ Ext<F> sm[EV_THREADS];
+               const Ext<F>* __restrict__ tab, int Q, Ext<F>* __restrict__ partial) {
+    __shared__ Ext<F> sm[EV_THREADS / 32];
     const uint64_t poly = blockIdx.y, npoly = gridDim.y, nblk = gridDim.x;
-    const uint64_t i0 = (uint64_t)blockIdx.x * EV_BLOCK + (uint64_t)threadIdx.x * EV_SEG;
+    const uint64_t per_q = EV_THREADS + EV_SEG + nblk;
+    const uint64_t i0 = (uint64_t)blockIdx.x * EV_BLOCK + threadIdx.x;
     Ext<F> cf[EV_SEG];
 #pragma unroll
-    for (int k = 0; k < EV_SEG; k++) cf[k] = (i0 + k < n) ? load_coef<F, CD>(coef, stride, poly, off + (i0 + k) * step) : ext_zero<F>();
+    for (int k = 0; k < EV_SEG; k++) {
+        const uint64_t i = i0 + (uint64_t)k * EV_THREADS;
+        cf[k] = i < n ? load_coef<F, CD>(coef, stride, poly, off + i * step) : ext_zero<F>();
+    }
     for (int q = 0; q < Q; q++) {
-        const Ext<F> zq = z[q];
-        Ext<F> acc = cf[EV_SEG - 1];
+        const Ext<F>* tq = tab + (uint64_t)q * per_q;
+        Ext<F> acc = cf[0];
 #pragma unroll
-        for (int k = EV_SEG - 2; k >= 0; k--) acc = ext_add(ext_mul(acc, zq), cf[k]);
-        Ext<F> zseg = zq;
+        for (int k = 1; k < EV_SEG; k++) acc = ext_add(acc, coef_times<F, CD>(cf[k], tq[EV_THREADS + k]));
+        acc = ext_mul(acc, tq[threadIdx.x]);
+        // block sum: warp shuffles, then one value per warp through shared memory
 #pragma unroll
-        for (int k = 1; k < EV_SEG; k <<= 1) zseg = ext_mul(zseg, zseg);
-        Ext<F> r = block_tree<F>(acc, zseg, sm);
-        if (threadIdx.x == 0) partial[((uint64_t)q * npoly + poly) * nblk + blockIdx.x] = r;
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            Ext<F> o;
+#pragma unroll
+            for (int d = 0; d < F::D; d++) o.c[d] = __shfl_down_sync(0xffffffffu, acc.c[d], ofs);
+            acc = ext_add(acc, o);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Ext<F> r = sm[0];
+#pragma unroll
+            for (int w = 1; w < EV_THREADS / 32; w++) r = ext_add(r, sm[w]);
+            partial[((uint64_t)q * npoly + poly) * nblk + blockIdx.x] = ext_mul(r, tq[EV_THREADS + EV_SEG + blockIdx.x]);
+        }
     }
 }
 
-// out[q*npoly + poly] = sum_b partial[(q*npoly+poly)*nblk + b] * (z_q^EV_BLOCK)^b
+// out[pq] = sum_b partial[pq*nblk + b]
 template <class F>
 __global__ void __launch_bounds__(EV_THREADS)
-k_eval_final(const Ext<F>* __restrict__ partial, uint64_t nblk, uint64_t npoly, const Ext<F>* __restrict__ z, Ext<F>* __restrict__ out) {
-    __shared__ Ext<F> sm[EV_THREADS];
+k_eval_final(const Ext<F>* __restrict__ partial, uint64_t nblk, Ext<F>* __restrict__ out) {
+    __shared__ Ext<F> sm[EV_THREADS / 32];
     const uint64_t pq = blockIdx.x;
-    const uint64_t q = pq / npoly;
-    const Ext<F> Z = ext_pow<F>(z[q], EV_BLOCK);
-    const uint64_t seg = (nblk + EV_THREADS - 1) / EV_THREADS;
-    const uint64_t b0 = (uint64_t)threadIdx.x * seg;
     Ext<F> acc = ext_zero<F>();
-    for (uint64_t k = seg; k-- > 0;) {
-        uint64_t b = b0 + k;
-        Ext<F> v = b < nblk ? partial[pq * nblk + b] : ext_zero<F>();
-        acc = ext_add(ext_mul(acc, Z), v);
+    for (uint64_t b = threadIdx.x; b < nblk; b += EV_THREADS) acc = ext_add(acc, partial[pq * nblk + b]);
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        Ext<F> o;
+#pragma unroll
+        for (int d = 0; d < F::D; d++) o.c[d] = __shfl_down_sync(0xffffffffu, acc.c[d], ofs);
+        acc = ext_add(acc, o);
     }
-    Ext<F> r = block_tree<F>(acc, ext_pow<F>(Z, seg), sm);
-    if (threadIdx.x == 0) out[pq] = r;
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Ext<F> r = sm[0];
+        for (int w = 1; w < EV_THREADS / 32; w++) r = ext_add(r, sm[w]);
+        out[pq] = r;
+    }
 }
 
 // Evaluate `npoly` polynomials (coefficient degree CD = 1 base / F::D extension) at Q extension
@@ -152,16 +183,24 @@ int eval_points(Ctx* c, const typename F::T* d_coef, uint64_t stride, uint64_t o
         return MS_OK;
     }
     const uint64_t nblk = (n + EV_BLOCK - 1) / EV_BLOCK;
-    Scratch dz(c), part(c), dout(c);
+    const uint64_t per_q = EV_THREADS + EV_SEG + nblk;
+    Scratch dz(c), tab(c), part(c), dout(c);
     MS_TRY(dz.alloc(Q * sizeof(Ext<F>)));
+    MS_TRY(tab.alloc((size_t)Q * per_q * sizeof(Ext<F>)));
     MS_TRY(part.alloc((size_t)Q * npoly * nblk * sizeof(Ext<F>)));
     MS_TRY(dout.alloc((size_t)Q * npoly * sizeof(Ext<F>)));
     MS_CUDA(c, cudaMemcpyAsync(dz.p, z_host, Q * sizeof(Ext<F>), cudaMemcpyHostToDevice, c->stream));
-    dim3 grid((unsigned)nblk, (unsigned)npoly);
-    if (coefdeg == 1) k_eval_partial<F, 1><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, dz.as<Ext<F>>(), Q, part.as<Ext<F>>());
-    else k_eval_partial<F, F::D><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, dz.as<Ext<F>>(), Q, part.as<Ext<F>>());
+    prof_begin(c, "k_eval_powers");
+    k_eval_powers<F><<<(unsigned)((per_q * Q + 127) / 128), 128, 0, c->stream>>>(dz.as<Ext<F>>(), Q, nblk, tab.as<Ext<F>>());
+    prof_end(c);
     MS_LAUNCH_CHECK(c);
-    k_eval_final<F><<<(unsigned)(Q * npoly), EV_THREADS, 0, c->stream>>>(part.as<Ext<F>>(), nblk, npoly, dz.as<Ext<F>>(), dout.as<Ext<F>>());
+    dim3 grid((unsigned)nblk, (unsigned)npoly);
+    prof_begin(c, "k_eval_partial");
+    if (coefdeg == 1) k_eval_partial<F, 1, 0><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, tab.as<Ext<F>>(), Q, part.as<Ext<F>>());
+    else k_eval_partial<F, F::D, 0><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, tab.as<Ext<F>>(), Q, part.as<Ext<F>>());
+    prof_end(c);
+    MS_LAUNCH_CHECK(c);
+    k_eval_final<F><<<(unsigned)(Q * npoly), EV_THREADS, 0, c->stream>>>(part.as<Ext<F>>(), nblk, dout.as<Ext<F>>());
     MS_LAUNCH_CHECK(c);
     MS_CUDA(c, cudaMemcpyAsync(out_host, dout.p, (size_t)Q * npoly * sizeof(Ext<F>), cudaMemcpyDeviceToHost, c->stream));
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -182,11 +221,21 @@ int deep_open(Ctx* c, const typename F::T* d_coef, uint64_t stride, uint64_t n, 
 // out = 1 + (largest index with a non-zero coordinate in any of `planes` planes), 0 for the zero poly
 template <class F>
 __global__ void k_poly_len(const typename F::T* __restrict__ p, uint64_t stride, int planes, uint64_t n, unsigned long long* out) {
+    __shared__ unsigned long long sm[8];
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     bool nz = false;
-    for (int d = 0; d < planes; d++) nz = nz || (p[(uint64_t)d * stride + i] != 0);
-    if (nz) atomicMax(out, (unsigned long long)(i + 1));
+    if (i < n)
+        for (int d = 0; d < planes; d++) nz = nz || (p[(uint64_t)d * stride + i] != 0);
+    // one atomic per block: the highest non-zero lane of the highest non-empty warp
+    const unsigned ballot = __ballot_sync(0xffffffffu, nz);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sm[warp] = ballot ? (unsigned long long)(i + (31 - __clz(ballot)) + 1) : 0ULL;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = sm[w] > m ? sm[w] : m;
+        if (m) atomicMax(out, m);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ suffix scan

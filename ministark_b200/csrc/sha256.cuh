@@ -16,6 +16,31 @@ __host__ __device__ __forceinline__ uint32_t sha_rotr(uint32_t x, int n) {
 #endif
 }
 
+// SHA-256 is all rotates, 3-input logic and adds: on sm_100a every one of those issues on the ALU
+// pipe (SHF / LOP3 / IADD3, one warp instruction per two cycles) while the FMA pipe idles.  A rotate
+// is also  hi(x * 2^(32-n)) + lo(x * 2^(32-n)),  i.e. IMAD.HI + IMAD on the FMA pipe.  The multiplier
+// is read from constant memory so that ptxas cannot strength-reduce it back into a shift.  Which
+// rotates take this route is a tuning mask (MS_SHA_FMA_MASK: 1 Sigma1, 2 Sigma0, 4 sigma0, 8 sigma1).
+#ifndef MS_SHA_FMA_MASK
+#define MS_SHA_FMA_MASK 0
+#endif
+#ifdef __CUDACC__
+__constant__ uint32_t SHA_ROT_MUL[32] = {
+    0u,        1u << 31, 1u << 30, 1u << 29, 1u << 28, 1u << 27, 1u << 26, 1u << 25, 1u << 24, 1u << 23, 1u << 22,
+    1u << 21,  1u << 20, 1u << 19, 1u << 18, 1u << 17, 1u << 16, 1u << 15, 1u << 14, 1u << 13, 1u << 12, 1u << 11,
+    1u << 10,  1u << 9,  1u << 8,  1u << 7,  1u << 6,  1u << 5,  1u << 4,  1u << 3,  1u << 2,  1u << 1};
+#endif
+template <int WHICH>
+__host__ __device__ __forceinline__ uint32_t sha_rot(uint32_t x, int n) {
+#ifdef __CUDA_ARCH__
+    if (MS_SHA_FMA_MASK & WHICH) {
+        const uint32_t c = SHA_ROT_MUL[n];
+        return __umulhi(x, c) + x * c;
+    }
+#endif
+    return sha_rotr(x, n);
+}
+
 __host__ __device__ __forceinline__ void sha256_init(uint32_t st[8]) {
     st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
     st[4] = 0x510e527f; st[5] = 0x9b05688c; st[6] = 0x1f83d9ab; st[7] = 0x5be0cd19;
@@ -41,15 +66,15 @@ __host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_
             wi = w[i];
         } else {
             uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-            uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
-            uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+            uint32_t s0 = sha_rot<4>(w15, 7) ^ sha_rot<4>(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = sha_rot<8>(w2, 17) ^ sha_rot<8>(w2, 19) ^ (w2 >> 10);
             wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
             w[i & 15] = wi;
         }
-        uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+        uint32_t S1 = sha_rot<1>(e, 6) ^ sha_rot<1>(e, 11) ^ sha_rot<1>(e, 25);
         uint32_t ch = (e & f) ^ (~e & g);
         uint32_t t1 = h + S1 + ch + K[i] + wi;
-        uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+        uint32_t S0 = sha_rot<2>(a, 2) ^ sha_rot<2>(a, 13) ^ sha_rot<2>(a, 22);
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
         uint32_t t2 = S0 + mj;
         h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;

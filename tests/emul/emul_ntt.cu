@@ -122,7 +122,7 @@ static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, 
     if (two) {
         NttTile<F> g2{};
         g2.src = g1.dst; g2.src_stride = g1.dst_stride; g2.dst = out.data(); g2.dst_stride = N << logB;
-        g2.tw = wtab.data(); g2.a = pl.b; g2.beta = pl.logR2 + logB; g2.logB = logB; g2.mode = 1;
+        g2.tw = wtab.data(); g2.a = pl.b; g2.beta = pl.logR2 + logB; g2.logB = logB; g2.mode = 1; g2.plain = 1;
         g2.a1 = pl.a; g2.beta1 = g1.beta; g2.logR1 = pl.logR1;
         g2.tiles = (uint32_t)((1ULL << pl.a) >> pl.logR2); g2.cols = (uint32_t)cols;
         run_any<F>(g2);
