@@ -167,6 +167,34 @@ int32_t ms_stark_prove(ms_ctx* ctx, const ms_stark_params* p, const void* trace_
 /* Same with the trace already resident on the device (column-major W x N, stride n). */
 int32_t ms_stark_prove_device(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
                               const void* constraint_matrix_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len);
+/* Multi-GPU commitments.  The prover runs as one replica per GPU; the two stages whose
+ * work shards -- the trace tree (row ranges) and the LDE + its tree (column shards -> all-to-all -> row
+ * ranges -> subtree roots -> all-gather) -- are delegated to the host through these hooks, which is
+ * where the NCCL exchange lives (ministark_b200/sharded.py drives it with torch.distributed).  A hook
+ * returns an MS_* status and must leave the 32 root bytes in root32.  Pointers are device pointers
+ * valid on the context's stream.  Replaces the same call sites as ms_merkle_commit / ms_coset_lde
+ * (src/starks.rs:70-72 and src/starks.rs:82-94). */
+typedef struct ms_commit_hooks {
+    void* user;
+    int32_t (*trace_commit)(void* user, const void* d_trace_colmajor, uint64_t n, uint64_t w, uint8_t* root32);
+    int32_t (*lde_commit)(void* user, const void* d_coeffs_colmajor, uint64_t n, uint64_t cols, uint64_t blowup,
+                          uint64_t shift, uint8_t* root32);
+} ms_commit_hooks;
+/* ms_stark_prove_device with the two commitments routed through `hooks` (NULL members = local). */
+int32_t ms_stark_prove_hooked(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
+                              const void* constraint_matrix_host, uint64_t t, const ms_commit_hooks* hooks,
+                              uint8_t* proof_out, uint64_t* proof_len);
+/* Upper levels of a tree whose level-`n` digests already exist (8 words each, device): hashes groups of
+ * `inner_children` digests until one is left (src/merkle.rs:133-140).  Used to join the subtree roots
+ * the ranks gathered.  n must be a power of inner_children. */
+int32_t ms_merkle_reduce(ms_ctx* ctx, const uint32_t* d_digests, uint64_t n, uint64_t inner_children, uint8_t* root32);
+
+/* One rank's share of MerkleTree::new: leaf groups of an aligned, contiguous row range (rows x width
+ * elements starting at d_data, same layout as ms_merkle_commit) hashed and reduced while whole groups of
+ * inner_children digests remain; *n_out (< inner_children) digests are left in d_digests_out. */
+int32_t ms_merkle_subtree(ms_ctx* ctx, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width, int32_t deg,
+                          uint64_t leafs_per_node, uint64_t inner_children, uint32_t* d_digests_out, uint64_t* n_out);
+
 /* per-stage device times (ms) of the last ms_stark_prove* call: fills up to `cap` entries, returns count.
  * names[i] points to static strings. */
 int32_t ms_stark_last_timings(ms_ctx* ctx, const char** names, float* ms, int32_t cap);

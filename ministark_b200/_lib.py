@@ -25,6 +25,15 @@ class StarkParams(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("security_bits", "blowup_factor", "steps", "trace_columns", "inner_children")]
 
 
+TRACE_COMMIT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint8))
+LDE_COMMIT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint8))
+
+
+class CommitHooks(C.Structure):
+    """ms_commit_hooks (include/ministark.h)"""
+    _fields_ = [("user", C.c_void_p), ("trace_commit", TRACE_COMMIT_FN), ("lde_commit", LDE_COMMIT_FN)]
+
+
 # every symbol include/ministark.h declares: name -> (restype, argtypes)
 _u64, _i32, _vp, _sz = C.c_uint64, C.c_int32, C.c_void_p, C.c_size_t
 SIGNATURES = {
@@ -58,6 +67,9 @@ SIGNATURES = {
     "ms_stark_proof_bound": (_u64, [_i32, C.POINTER(StarkParams), _u64, _u64]),
     "ms_stark_prove": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_device": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "ms_stark_prove_hooked": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
+    "ms_merkle_subtree": (_i32, [_vp, _vp, _u64, _u64, _u64, _i32, _u64, _u64, _vp, C.POINTER(_u64)]),
+    "ms_merkle_reduce": (_i32, [_vp, _vp, _u64, _u64, _vp]),
     "ms_stark_last_timings": (_i32, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i32]),
 }
 

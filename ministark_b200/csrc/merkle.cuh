@@ -226,28 +226,8 @@ inline void digest_words_to_bytes(const uint32_t* w, uint8_t* out) {
     }
 }
 
-// MerkleTree::new.  d_nodes: caller buffer for all nodes or nullptr (scratch); root32: host or nullptr.
-template <class F>
-int merkle_commit(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t rows, uint64_t width, int deg,
-                  uint64_t lpn, uint64_t k, uint32_t* d_nodes, uint8_t* root32) {
-    const uint64_t n_elems = rows * width;
-    if (lpn == 0 || n_elems == 0 || n_elems % lpn) return fail(c, MS_ERR_BAD_SHAPE, "leaf count %llu not divisible by leafs_per_node %llu (merkle.rs:99)", (unsigned long long)n_elems, (unsigned long long)lpn);
-    const uint64_t n1 = n_elems / lpn;
-    const uint64_t total = merkle_node_count(n1, k);
-    if (total == 0 || (k != 2 && k != 4 && k != 8 && k != 16))
-        return fail(c, MS_ERR_BAD_SHAPE, "Tree is not full! %llu leaf groups, inner_children %llu (merkle.rs:93-104)", (unsigned long long)n1, (unsigned long long)k);
-    if (deg != 1 && deg != F::D) return fail(c, MS_ERR_BAD_SHAPE, "deg must be 1 or the extension degree");
-    Scratch own(c);
-    if (!d_nodes) {
-        MS_TRY(own.alloc(total * 32));
-        d_nodes = own.as<uint32_t>();
-    }
-    unsigned blocks = (unsigned)((n1 + LEAF_THREADS - 1) / LEAF_THREADS);
-    prof_begin(c, "k_leaf_hash");
-    if (deg == 1) k_leaf_hash<F, 1><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
-    else k_leaf_hash<F, F::D><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
-    prof_end(c);
-    MS_LAUNCH_CHECK(c);
+// levels above the first: d_nodes holds `n1` level-1 digests followed by room for every upper level
+inline int merkle_upper_levels(Ctx* c, uint32_t* d_nodes, uint64_t n1, uint64_t k) {
     uint64_t src = 0, lv = n1;
     while (lv > 1) {
         uint64_t np = lv / k;
@@ -266,12 +246,110 @@ int merkle_commit(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t
         src += lv;
         lv = np;
     }
+    return MS_OK;
+}
+
+// join already hashed digests (e.g. the subtree roots gathered from the other GPUs) into one root
+inline int merkle_reduce(Ctx* c, const uint32_t* d_digests, uint64_t n, uint64_t k, uint8_t* root32) {
+    const uint64_t total = merkle_node_count(n, k);
+    if (total == 0 || (k != 2 && k != 4 && k != 8 && k != 16) || !root32)
+        return fail(c, MS_ERR_BAD_SHAPE, "merkle_reduce: %llu digests do not form a full %llu-ary tree", (unsigned long long)n, (unsigned long long)k);
+    Scratch nodes(c);
+    MS_TRY(nodes.alloc(total * 32));
+    MS_CUDA(c, cudaMemcpyAsync(nodes.p, d_digests, n * 32, cudaMemcpyDeviceToDevice, c->stream));
+    MS_TRY(merkle_upper_levels(c, nodes.as<uint32_t>(), n, k));
+    uint32_t w[8];
+    MS_CUDA(c, cudaMemcpyAsync(w, nodes.as<uint32_t>() + (total - 1) * 8, 32, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    digest_words_to_bytes(w, root32);
+    return MS_OK;
+}
+
+template <class F>
+int merkle_leaf_level(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t width, int deg, uint64_t lpn, uint64_t n1,
+                      uint32_t* d_nodes) {
+    unsigned blocks = (unsigned)((n1 + LEAF_THREADS - 1) / LEAF_THREADS);
+    prof_begin(c, "k_leaf_hash");
+    if (deg == 1) k_leaf_hash<F, 1><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
+    else k_leaf_hash<F, F::D><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
+    prof_end(c);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+
+// MerkleTree::new.  d_nodes: caller buffer for all nodes or nullptr (scratch); root32: host or nullptr.
+template <class F>
+int merkle_commit(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t rows, uint64_t width, int deg,
+                  uint64_t lpn, uint64_t k, uint32_t* d_nodes, uint8_t* root32) {
+    const uint64_t n_elems = rows * width;
+    if (lpn == 0 || n_elems == 0 || n_elems % lpn) return fail(c, MS_ERR_BAD_SHAPE, "leaf count %llu not divisible by leafs_per_node %llu (merkle.rs:99)", (unsigned long long)n_elems, (unsigned long long)lpn);
+    const uint64_t n1 = n_elems / lpn;
+    const uint64_t total = merkle_node_count(n1, k);
+    if (total == 0 || (k != 2 && k != 4 && k != 8 && k != 16))
+        return fail(c, MS_ERR_BAD_SHAPE, "Tree is not full! %llu leaf groups, inner_children %llu (merkle.rs:93-104)", (unsigned long long)n1, (unsigned long long)k);
+    if (deg != 1 && deg != F::D) return fail(c, MS_ERR_BAD_SHAPE, "deg must be 1 or the extension degree");
+    Scratch own(c);
+    if (!d_nodes) {
+        MS_TRY(own.alloc(total * 32));
+        d_nodes = own.as<uint32_t>();
+    }
+    MS_TRY(merkle_leaf_level<F>(c, d_data, stride, width, deg, lpn, n1, d_nodes));
+    MS_TRY(merkle_upper_levels(c, d_nodes, n1, k));
     if (root32) {
         uint32_t w[8];
         MS_CUDA(c, cudaMemcpyAsync(w, d_nodes + (total - 1) * 8, 32, cudaMemcpyDeviceToHost, c->stream));
         MS_CUDA(c, cudaStreamSynchronize(c->stream));
         digest_words_to_bytes(w, root32);
     }
+    return MS_OK;
+}
+
+// A rank's share of a tree: hash the leaf groups of a contiguous, aligned range of
+// rows and climb while whole groups of k digests remain.  Leaves *n_out < k digests (1 when the range
+// is itself a full subtree) in d_out; the caller gathers every rank's digests and joins them with
+// merkle_reduce.  The range must hold a power-of-two number of leaf groups.
+template <class F>
+int merkle_subtree(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t rows, uint64_t width, int deg, uint64_t lpn,
+                   uint64_t k, uint32_t* d_out, uint64_t* n_out) {
+    const uint64_t n_elems = rows * width;
+    if (lpn == 0 || n_elems == 0 || n_elems % lpn) return fail(c, MS_ERR_BAD_SHAPE, "leaf count %llu not divisible by leafs_per_node %llu (merkle.rs:99)", (unsigned long long)n_elems, (unsigned long long)lpn);
+    const uint64_t n1 = n_elems / lpn;
+    if (!is_pow2(n1) || (k != 2 && k != 4 && k != 8 && k != 16)) return fail(c, MS_ERR_BAD_SHAPE, "subtree of %llu leaf groups, inner_children %llu", (unsigned long long)n1, (unsigned long long)k);
+    if (deg != 1 && deg != F::D) return fail(c, MS_ERR_BAD_SHAPE, "deg must be 1 or the extension degree");
+    uint64_t total = 0, lv = n1;
+    while (true) {
+        total += lv;
+        if (lv == 1 || lv % k) break;
+        lv /= k;
+    }
+    const uint64_t rem = lv, full = n1 / rem;  // `rem` independent full subtrees of `full` leaf groups
+    Scratch nodes(c);
+    MS_TRY(nodes.alloc(total * 32));
+    uint32_t* d_nodes = nodes.as<uint32_t>();
+    MS_TRY(merkle_leaf_level<F>(c, d_data, stride, width, deg, lpn, n1, d_nodes));
+    // the same level-by-level climb as merkle_upper_levels, stopping at `rem` digests
+    uint64_t src = 0;
+    lv = n1;
+    while (lv > rem) {
+        uint64_t np = lv / k;
+        const uint32_t* ch = d_nodes + src * 8;
+        uint32_t* pa = d_nodes + (src + lv) * 8;
+        unsigned nb = (unsigned)((np + 255) / 256);
+        prof_begin(c, "k_node_hash");
+        switch (k) {
+            case 2: k_node_hash<2><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
+            case 4: k_node_hash<4><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
+            case 8: k_node_hash<8><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
+            default: k_node_hash<16><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
+        }
+        prof_end(c);
+        MS_LAUNCH_CHECK(c);
+        src += lv;
+        lv = np;
+    }
+    (void)full;
+    MS_CUDA(c, cudaMemcpyAsync(d_out, d_nodes + src * 8, rem * 32, cudaMemcpyDeviceToDevice, c->stream));
+    if (n_out) *n_out = rem;
     return MS_OK;
 }
 

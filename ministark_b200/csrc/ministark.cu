@@ -247,6 +247,23 @@ int32_t ms_stark_prove_device(ms_ctx* c, const ms_stark_params* p, const void* d
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }
+int32_t ms_stark_prove_hooked(ms_ctx* c, const ms_stark_params* p, const void* d_trace_cm, uint64_t n, uint64_t w,
+                              const void* cmat_host, uint64_t t, const ms_commit_hooks* hooks, uint8_t* proof_out,
+                              uint64_t* proof_len) {
+    if (!c->prover) c->prover = new ms::ProverState();
+#define CALL(F) stark_prove<F>(c, c->prover, *p, nullptr, d_trace_cm, n, w, (const F::T*)cmat_host, t, proof_out, proof_len, hooks)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+int32_t ms_merkle_subtree(ms_ctx* c, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width, int32_t deg,
+                          uint64_t lpn, uint64_t k, uint32_t* d_out, uint64_t* n_out) {
+#define CALL(F) merkle_subtree<F>(c, (const F::T*)d_data, stride, rows, width, deg, lpn, k, d_out, n_out)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+int32_t ms_merkle_reduce(ms_ctx* c, const uint32_t* d_digests, uint64_t n, uint64_t k, uint8_t* root32) {
+    return merkle_reduce(c, d_digests, n, k, root32);
+}
 int32_t ms_stark_last_timings(ms_ctx* c, const char** names, float* msv, int32_t cap) {
     if (!c->prover) return 0;
     int n = 0;

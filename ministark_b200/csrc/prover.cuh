@@ -101,7 +101,8 @@ uint64_t proof_size_bound(const ms_stark_params& p, const StarkDerived& d, uint6
 
 template <class F>
 int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* trace_rm_host, const void* d_trace_cm_in,
-                uint64_t n, uint64_t w, const typename F::T* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
+                uint64_t n, uint64_t w, const typename F::T* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len,
+                const ms_commit_hooks* hooks = nullptr) {
     using T = typename F::T;
     using E = Ext<F>;
     constexpr int D = F::D;
@@ -153,7 +154,12 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     tm.end();
     tm.begin("trace_commit");
     uint8_t trace_root[32], lde_root[32];
-    MS_TRY(merkle_commit<F>(c, d_trace, n, n, w, 1, lpn, kk, nullptr, trace_root));
+    if (hooks && hooks->trace_commit) {
+        int rc = hooks->trace_commit(hooks->user, d_trace, n, w, trace_root);
+        if (rc != MS_OK) return fail(c, rc, "trace_commit hook failed");
+    } else {
+        MS_TRY(merkle_commit<F>(c, d_trace, n, n, w, 1, lpn, kk, nullptr, trace_root));
+    }
     tm.end();
     TR(merlin.add_bytes(trace_root, 32));
     // ---- 1.2 LDE of trace + constraint polynomials and its commitment            starks.rs:80-95
@@ -168,16 +174,23 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     tm.begin("constraints");
     MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
     tm.end();
-    MS_TRY(lde.alloc(C * L * sizeof(T)));
-    tm.begin("lde");
-    MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, C, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91
-    tm.end();
-    tm.begin("lde_commit");
-    MS_TRY(merkle_commit<F>(c, lde.as<T>(), L, L, C, 1, lpn, kk, nullptr, lde_root));  // starks.rs:92-94
-    tm.end();
+    if (hooks && hooks->lde_commit) {
+        tm.begin("lde+commit(hook)");
+        int rc = hooks->lde_commit(hooks->user, coeffs.as<T>(), n, C, B, (uint64_t)shift, lde_root);
+        if (rc != MS_OK) return fail(c, rc, "lde_commit hook failed");
+        tm.end();
+    } else {
+        MS_TRY(lde.alloc(C * L * sizeof(T)));
+        tm.begin("lde");
+        MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, C, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91
+        tm.end();
+        tm.begin("lde_commit");
+        MS_TRY(merkle_commit<F>(c, lde.as<T>(), L, L, C, 1, lpn, kk, nullptr, lde_root));  // starks.rs:92-94
+        tm.end();
+        cudaFreeAsync(lde.p, c->stream);  // the LDE tree is never opened by the reference
+        lde.p = nullptr;
+    }
     TR(merlin.add_bytes(lde_root, 32));
-    cudaFreeAsync(lde.p, c->stream);  // the LDE tree is never opened by the reference
-    lde.p = nullptr;
     // ---- 1.3 mixing                                                                  starks.rs:108-119
     T r;
     TR(challenge_base(&r));

@@ -1,0 +1,247 @@
+"""Multi-GPU commitments (ministark_b200/sharded.py).
+
+CPU part: the sharding plans, and the whole exchange (grouped send/recv, subtree digests, all-gather,
+join) driven over `gloo` with world size 2 and 4, with the oracle standing in for the CUDA calls, so
+the host logic is covered without a GPU.  GPU part: the hooked prover at world size 1 must give the
+bytes of the plain prover, and with >= 2 GPUs the sharded proof must equal the single-GPU one."""
+import ctypes
+import hashlib
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from ministark_b200.sharded import ShardedCommitter, SubtreePlan, column_ranges, exchange_plan, owner_of_column
+
+GL = 0
+
+
+def test_column_ranges_cover_and_balance():
+    for cols in (1, 6, 32, 33, 64):
+        for world in (1, 2, 4, 8):
+            r = column_ranges(cols, world)
+            assert r[0][0] == 0 and r[-1][1] == cols and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+            for c in range(cols):
+                g = owner_of_column(c, cols, world)
+                assert r[g][0] <= c < r[g][1]
+
+
+def test_exchange_plan_is_a_permutation():
+    cols, world = 12, 4
+    sent, received = set(), set()
+    for rank in range(world):
+        sends, recvs = exchange_plan(cols, world, rank)
+        for _lc, c, h in sends:
+            assert owner_of_column(c, cols, world) == rank and h != rank
+            sent.add((c, rank, h))
+        for c, g in recvs:
+            assert owner_of_column(c, cols, world) == g and g != rank
+            received.add((c, g, rank))
+    assert sent == received and len(sent) == cols * (world - 1)
+
+
+@pytest.mark.parametrize("groups,k,world,levels,left", [(1 << 10, 2, 8, 7, 1), (1 << 10, 4, 4, 4, 1), (1 << 10, 4, 2, 4, 2),
+                                                       (1 << 9, 8, 8, 2, 1), (1 << 9, 8, 2, 2, 4), (16, 2, 1, 4, 1)])
+def test_subtree_plan(groups, k, world, levels, left):
+    p = SubtreePlan.make(groups, k, world)
+    assert (p.levels_local, p.digests_per_rank) == (levels, left)
+
+
+def test_subtree_plan_rejects_non_full_trees():
+    with pytest.raises(ValueError):
+        SubtreePlan.make(1 << 9, 4, 1)  # 2^9 leaf groups are not a power of 4 (merkle.rs:93-104)
+    with pytest.raises(ValueError):
+        SubtreePlan.make(24, 2, 4)
+
+
+# ------------------------------------------------------------------------------------------ gloo
+class OracleOps:
+    """Test stand-in for CudaOps: same interface, CPU tensors, compute by the oracle."""
+
+    elem = 8
+
+    def __init__(self, field):
+        from oracle import oracle as O
+
+        self.O, self.field = O, field
+
+    def empty(self, *shape):
+        import torch
+
+        return torch.zeros(*shape, dtype=torch.int64)
+
+    def empty_digests(self, n):
+        import torch
+
+        return torch.zeros(n, 8, dtype=torch.int32)
+
+    @staticmethod
+    def _view(ptr, count):
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(count,))
+
+    def lde(self, coeffs_ptr, n, ncols, blowup, shift, out):
+        import torch
+
+        coeffs = self._view(coeffs_ptr, n * ncols).reshape(ncols, n).copy()
+        ev = self.O.coset_lde(self.field, coeffs, n * blowup, shift)  # [L, ncols]
+        out[:ncols] = torch.from_numpy(np.ascontiguousarray(ev.T).view(np.int64))
+
+    @staticmethod
+    def _words(digest: bytes):
+        return np.frombuffer(digest, dtype=">u4").astype(np.uint32).view(np.int32)
+
+    def subtree(self, data_ptr, stride, rows, width, lpn, k, out_digests):
+        import torch
+
+        cols = [self._view(data_ptr + c * stride * 8, rows) for c in range(width)]
+        flat = np.stack(cols, axis=1).reshape(-1)  # row-major flattening
+        groups = flat.size // lpn
+        lv = groups
+        while lv > 1 and lv % k == 0:
+            lv //= k
+        per = flat.size // lv
+        for i in range(lv):
+            out_digests[i] = torch.from_numpy(self._words(self.O.merkle(flat[i * per:(i + 1) * per], lpn, k)).copy())
+        return lv
+
+    def reduce(self, digests, n, k):
+        level = [digests[i].numpy().view(np.uint32).astype(">u4").tobytes() for i in range(n)]
+        while len(level) > 1:
+            level = [hashlib.sha256(b"".join(level[i:i + k])).digest() for i in range(0, len(level), k)]
+        return level[0]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, n, cols, blowup, k, w, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.synth import synth_trace
+
+        coeffs = np.ascontiguousarray(synth_trace(GL, n, cols, seed=5).T)  # [cols, n], same on every rank
+        com = ShardedCommitter(OracleOps(GL), cols, k, dist)
+        lde_root = com.lde_commit(coeffs.ctypes.data, n, cols, blowup, 7)
+        trace_cm = np.ascontiguousarray(synth_trace(GL, n, w, seed=9).T)  # [w, n]
+        trace_root = com.trace_commit(trace_cm.ctypes.data, n, w)
+        q.put((rank, lde_root, trace_root, com.stats["exchange_bytes_out"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,k", [(2, 2), (4, 2), (2, 4), (4, 4)])
+def test_sharded_commit_over_gloo_matches_oracle(world, k, oracle):
+    import torch.multiprocessing as mp
+
+    from tests.synth import synth_trace
+
+    n, cols, blowup, w = 256, 8, 4, 8
+    L = n * blowup
+    coeffs = np.ascontiguousarray(synth_trace(GL, n, cols, seed=5).T)
+    want_lde = oracle.merkle(oracle.coset_lde(GL, coeffs, L, 7).reshape(-1), cols, k)
+    want_trace = oracle.merkle(synth_trace(GL, n, w, seed=9).reshape(-1), cols, k)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, cols, blowup, k, w, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _rank, lde_root, trace_root, sent in got:
+        assert lde_root == want_lde
+        assert trace_root == want_trace
+        assert sent == (cols // world) * (world - 1) * (L // world) * 8  # L*C*s*(G-1)/G^2 per rank
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("field", [0, 1])
+@pytest.mark.parametrize("log_n,w,blowup,k", [(8, 4, 8, 2), (10, 8, 4, 8), (11, 4, 8, 4)])
+def test_hooked_prover_world1_equals_plain(field, log_n, w, blowup, k):
+    from ministark_b200 import Context
+    from ministark_b200._lib import StarkParams
+    from ministark_b200.sharded import stark_prove_sharded
+    from tests.synth import synth_linear_matrix, synth_trace
+
+    ctx = Context(field)
+    n = 1 << log_n
+    trace = synth_trace(field, n, w, seed=77 + log_n)
+    m = synth_linear_matrix(field, n, w)
+    params = StarkParams(40, blowup, n - 1, 2 * w, k)
+    want = ctx.stark_prove(params, trace, m)
+    out = np.empty(len(want) + 4096, dtype=np.uint8)
+    ln = stark_prove_sharded(ctx, params, ctx.to_device(np.ascontiguousarray(trace.T)), m, out)
+    assert out[:ln].tobytes() == want
+    ctx.close()
+
+
+def _nccl_worker(rank, world, port, log_n, w, blowup, k, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from ministark_b200 import Context
+        from ministark_b200._lib import StarkParams
+        from ministark_b200.sharded import stark_prove_sharded
+        from tests.synth import synth_linear_matrix, synth_trace
+
+        ctx = Context(0, rank)
+        n = 1 << log_n
+        trace = synth_trace(0, n, w, seed=123)
+        m = synth_linear_matrix(0, n, w)
+        params = StarkParams(40, blowup, n - 1, 2 * w, k)
+        out = np.empty(int(ctx.lib.ms_stark_proof_bound(0, params, n, 2 * w)), dtype=np.uint8)
+        ln = stark_prove_sharded(ctx, params, ctx.to_device(np.ascontiguousarray(trace.T)), m, out, dist)
+        q.put((rank, hashlib.sha256(out[:ln].tobytes()).hexdigest()))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [2, 4])
+def test_sharded_prover_multi_gpu_equals_single(k):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    if world == 3:
+        world = 2
+    from ministark_b200 import Context
+    from ministark_b200._lib import StarkParams
+    from tests.synth import synth_linear_matrix, synth_trace
+
+    log_n, w, blowup = 11, 4, 8  # N/2 = 4^5 trace leaf groups, L = 4^7 rows: full trees for k = 2 and 4
+    n = 1 << log_n
+    ctx = Context(0)
+    want = ctx.stark_prove(StarkParams(40, blowup, n - 1, 2 * w, k), synth_trace(0, n, w, seed=123), synth_linear_matrix(0, n, w))
+    ctx.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_nccl_worker, args=(r, world, port, log_n, w, blowup, k, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(h == hashlib.sha256(want).hexdigest() for _, h in got)
