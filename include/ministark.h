@@ -65,6 +65,10 @@ int32_t ms_profile_collect(ms_ctx* ctx, const char** names, float* total_ms, uin
 /* Display of the zero element: 0 -> "0" (ark-ff 0.5.0, default), 1 -> "" (ark-ff 0.4.x) */
 int32_t ms_set_zero_display(ms_ctx* ctx, int32_t empty);
 
+/* Device self-test of the lazy / Montgomery butterfly arithmetic (csrc/ntt.cuh Fast<F>) against exact host
+ * arithmetic on edge values and n_random random operand pairs; *n_bad = mismatches (0 expected). */
+int32_t ms_selftest_field_ops(ms_ctx* ctx, uint64_t n_random, uint64_t* n_bad);
+
 int32_t ms_dev_alloc(ms_ctx* ctx, size_t bytes, void** d_out);
 int32_t ms_dev_free(ms_ctx* ctx, void* d_ptr);
 int32_t ms_h2d(ms_ctx* ctx, void* d_dst, const void* src, size_t bytes);

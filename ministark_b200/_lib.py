@@ -46,6 +46,7 @@ SIGNATURES = {
     "ms_set_zero_display": (_i32, [_vp, _i32]),
     "ms_set_profiling": (_i32, [_vp, _i32]),
     "ms_profile_collect": (_i32, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), _i32]),
+    "ms_selftest_field_ops": (_i32, [_vp, _u64, C.POINTER(_u64)]),
     "ms_dev_alloc": (_i32, [_vp, _sz, C.POINTER(_vp)]),
     "ms_dev_free": (_i32, [_vp, _vp]),
     "ms_h2d": (_i32, [_vp, _vp, _vp, _sz]),

@@ -18,58 +18,99 @@
 namespace ms {
 
 constexpr int LEAF_THREADS = 128;
+constexpr int LEAF_WORDS = 32;  // per-thread message buffer: two SHA-256 blocks
 
-struct LeafRing {
-    uint32_t* w;     // word 0 of this thread; word i at w[i * LEAF_THREADS]
-    uint32_t base;   // byte offset of the first pending byte (0 or 64)
-    uint32_t pos;    // pending bytes
-    __device__ __forceinline__ void put(uint32_t byte) {
-        uint32_t k = (base + pos) & 127u;
-        reinterpret_cast<unsigned char*>(w + (k >> 2) * LEAF_THREADS)[3 - (k & 3u)] = (unsigned char)byte;
-        pos++;
+// ASCII of a 4-digit group: DEC4[c] = "0000".."9999" packed big-endian (first character in the top byte)
+__global__ void k_build_dec4(uint32_t* tab) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 10000) return;
+    uint32_t d0 = c / 1000, d1 = (c / 100) % 10, d2 = (c / 10) % 10, d3 = c % 10;
+    tab[c] = 0x30303030u + ((d0 << 24) | (d1 << 16) | (d2 << 8) | d3);
+}
+
+// The message of one leaf group is assembled as big-endian 32-bit words in a per-thread buffer in
+// shared memory (word i of thread t at buf[i*LEAF_THREADS + t]: conflict free).  `wp` points at the
+// word that holds the `fill` (0..3) pending bytes, left aligned, zeros below; everything beyond it is
+// don't-care.  Appending a string = one funnel shift per word + one store per word at compile-time
+// offsets from `wp`; no byte stores, no per-byte address arithmetic.
+struct LeafStream {
+    uint32_t* base;  // word 0 of this thread
+    uint32_t* wp;    // word with the pending bytes
+    uint32_t wr;     // complete words in the buffer
+    uint32_t fill;   // pending bytes in *wp
+    uint64_t total;  // message bytes so far
+
+    // X[0..NW): the string, left aligned, big-endian characters, zero padded; len <= 4*NW bytes
+    template <int NW>
+    __device__ __forceinline__ void append(const uint32_t (&X)[NW], uint32_t len) {
+        const uint32_t sh = 8u * fill;
+        const uint32_t part = *wp;
+        wp[0] = part | (X[0] >> sh);
+#pragma unroll
+        for (int k = 1; k < NW; k++) wp[k * LEAF_THREADS] = __funnelshift_r(X[k], X[k - 1], sh);
+        wp[NW * LEAF_THREADS] = __funnelshift_r(0u, X[NW - 1], sh);
+        const uint32_t t = fill + len;
+        wp += (t >> 2) * LEAF_THREADS;
+        wr += t >> 2;
+        fill = t & 3u;
+        total += len;
     }
 };
 
+constexpr uint32_t pack4(const char* s, int n, int off) {
+    uint32_t w = 0;
+    for (int i = 0; i < 4; i++) w = (w << 8) | (uint32_t)(off + i < n ? (unsigned char)s[off + i] : 0);
+    return w;
+}
 template <int N>
-__device__ __forceinline__ void put_lit(LeafRing& r, const char (&s)[N]) {
+__device__ __forceinline__ void put_lit(LeafStream& st, const char (&s)[N]) {
+    constexpr int len = N - 1;
+    static_assert(len >= 1 && len <= 16, "literals are appended in pieces of at most 16 bytes");
+    constexpr int NW = (len + 3) / 4;
+    uint32_t X[NW];
 #pragma unroll
-    for (int i = 0; i < N - 1; i++) r.put((unsigned char)s[i]);
+    for (int k = 0; k < NW; k++) X[k] = pack4(s, len, 4 * k);
+    st.append<NW>(X, (uint32_t)len);
 }
 
 // decimal digits of v (< 2^64), most significant first, no leading zeros; zero prints "0" (or
-// nothing when zero_empty)
-__device__ __forceinline__ void put_decimal(LeafRing& r, uint64_t v, int zero_empty) {
-    // split into four 5-digit limbs: v = ((l3 * 10^5 + l2) * 10^5 + l1) * 10^5 + l0
-    uint64_t hi = v / 10000000000ULL;          // < 1.85e9
-    uint64_t lo = v - hi * 10000000000ULL;     // < 1e10
-    uint32_t l3 = (uint32_t)hi / 100000u, l2 = (uint32_t)hi % 100000u;
-    uint32_t l1 = (uint32_t)(lo / 100000ULL), l0 = (uint32_t)(lo - (uint64_t)l1 * 100000ULL);
-    uint32_t limbs[4] = {l3, l2, l1, l0};
-    unsigned char d[20];
+// nothing when zero_empty): ark-ff Display of a field element
+__device__ __forceinline__ void put_decimal(LeafStream& st, uint64_t v, int zero_empty, const uint32_t* __restrict__ dec4) {
+    // five 4-digit groups: v = ((((g4)*10^4 + g3)*10^4 + g2)*10^4 + g1)*10^4 + g0
+    const uint64_t q1 = v / 100000000ULL;                       // < 1.85e11
+    const uint32_t r1 = (uint32_t)(v - q1 * 100000000ULL);      // < 1e8
+    const uint32_t g4 = (uint32_t)(q1 / 100000000ULL);          // < 1845
+    const uint32_t r2 = (uint32_t)(q1 - (uint64_t)g4 * 100000000ULL);
+    const uint32_t g3 = r2 / 10000u, g2 = r2 - g3 * 10000u;
+    const uint32_t g1 = r1 / 10000u, g0 = r1 - g1 * 10000u;
+    uint32_t A[5] = {__ldg(&dec4[g4]), __ldg(&dec4[g3]), __ldg(&dec4[g2]), __ldg(&dec4[g1]), __ldg(&dec4[g0])};
+    // leading zero characters
+    uint32_t skip;
+    const uint32_t z0 = A[0] ^ 0x30303030u;
+    if (z0) {
+        skip = (uint32_t)__clz(z0) >> 3;  // 0..3: the common case for 64-bit field elements
+    } else {
+        skip = 4;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t x = limbs[i];
-#pragma unroll
-        for (int k = 4; k >= 0; k--) {
-            uint32_t qd = x / 10u;
-            d[i * 5 + k] = (unsigned char)(x - qd * 10u);
-            x = qd;
+        for (int j = 1; j < 5; j++) {
+            const uint32_t z = A[j] ^ 0x30303030u;
+            if (skip == 4u * j) skip += z ? ((uint32_t)__clz(z) >> 3) : 4u;
+        }
+        if (skip == 20) skip = zero_empty ? 20 : 19;  // v == 0
+        // drop whole leading words (rare path; values below 10^16)
+        for (uint32_t wsk = skip >> 2; wsk; wsk--) {
+            A[0] = A[1]; A[1] = A[2]; A[2] = A[3]; A[3] = A[4]; A[4] = 0;
         }
     }
-    int skip = 0;
-    bool lead = true;
+    const uint32_t sb = 8u * (skip & 3u);
+    uint32_t X[5];
 #pragma unroll
-    for (int i = 0; i < 19; i++) {
-        lead = lead && (d[i] == 0);
-        skip += lead ? 1 : 0;
-    }
-    if (zero_empty && v == 0) skip = 20;
-#pragma unroll
-    for (int i = 0; i < 20; i++)
-        if (i >= skip) r.put('0' + d[i]);
+    for (int k = 0; k < 4; k++) X[k] = __funnelshift_l(A[k + 1], A[k], sb);
+    X[4] = A[4] << sb;
+    st.append<5>(X, 20u - skip);
 }
 
-// One "token" of the Display string of element coordinates (tokens keep each burst <= 26 bytes).
+// One "token" of the Display string of element coordinates.
 template <int DEG>
 struct Tokens;
 template <>
@@ -82,7 +123,7 @@ struct Tokens<2> {
 };
 template <>
 struct Tokens<4> {
-    static constexpr int PER_ELEM = 9;  // "QuadExtField(QuadExtField(" a " + " b " * u) + QuadExtField(" c " + " d " * u) * u)"
+    static constexpr int PER_ELEM = 11;  // "QuadExtField(" "QuadExtField(" a " + " b " * u) + " "QuadExtField(" c " + " d " * u)" " * u)"
 };
 
 // data layout: coordinate d of the element at (row, col) is data[(col*DEG + d)*stride + row];
@@ -90,52 +131,54 @@ struct Tokens<4> {
 template <class F, int DEG>
 __global__ void __launch_bounds__(LEAF_THREADS)
 k_leaf_hash(const typename F::T* __restrict__ data, uint64_t stride, uint64_t width, uint64_t lpn, uint64_t n_groups,
-            int zero_empty, uint32_t* __restrict__ nodes) {
-    __shared__ uint32_t ring[32 * LEAF_THREADS];
+            int zero_empty, const uint32_t* __restrict__ dec4, uint32_t* __restrict__ nodes) {
+    __shared__ uint32_t buf[LEAF_WORDS * LEAF_THREADS];
     const uint64_t g = (uint64_t)blockIdx.x * LEAF_THREADS + threadIdx.x;
     const bool live = g < n_groups;
-    LeafRing r;
-    r.w = ring + threadIdx.x;
-    r.base = 0;
-    r.pos = 0;
-#pragma unroll
-    for (int i = 0; i < 32; i++) r.w[i * LEAF_THREADS] = 0;
-    uint32_t st[8];
-    sha256_init(st);
+    LeafStream st;
+    st.base = buf + threadIdx.x;
+    st.wp = st.base;
+    st.wr = 0;
+    st.fill = 0;
+    st.total = 0;
+    st.base[0] = 0;
+    uint32_t h[8];
+    sha256_init(h);
     const uint64_t ntok = live ? lpn * Tokens<DEG>::PER_ELEM : 0;
-    uint64_t tok = 0, total_bytes = 0;
+    uint64_t tok = 0;
     uint64_t f = g * lpn;          // flat index of the current element
     uint64_t row = live ? f / width : 0, col = live ? f % width : 0;
     int sub = 0;                   // token index inside the current element
     bool padded = !live, finished = !live;
+    uint32_t end_words = 0;        // words of the padded message tail (16 or 32) once padded
     while (__any_sync(0xffffffffu, !finished)) {
         // ---- fill: append tokens until a full block is pending
-        while (r.pos < 64 && tok < ntok) {
-            const uint32_t before = r.pos;
+        while (st.wr < 16 && tok < ntok) {
             if (DEG == 1) {
-                put_decimal(r, (uint64_t)data[col * stride + row], zero_empty);
+                put_decimal(st, (uint64_t)data[col * stride + row], zero_empty, dec4);
             } else if (DEG == 2) {
                 switch (sub) {
-                    case 0: put_lit(r, "QuadExtField("); break;
-                    case 1: put_decimal(r, (uint64_t)data[(col * 2 + 0) * stride + row], zero_empty); break;
-                    case 2: put_lit(r, " + "); break;
-                    case 3: put_decimal(r, (uint64_t)data[(col * 2 + 1) * stride + row], zero_empty); break;
-                    default: put_lit(r, " * u)"); break;
+                    case 0: put_lit(st, "QuadExtField("); break;
+                    case 1: put_decimal(st, (uint64_t)data[(col * 2 + 0) * stride + row], zero_empty, dec4); break;
+                    case 2: put_lit(st, " + "); break;
+                    case 3: put_decimal(st, (uint64_t)data[(col * 2 + 1) * stride + row], zero_empty, dec4); break;
+                    default: put_lit(st, " * u)"); break;
                 }
             } else {
                 switch (sub) {
-                    case 0: put_lit(r, "QuadExtField(QuadExtField("); break;
-                    case 1: put_decimal(r, (uint64_t)data[(col * 4 + 0) * stride + row], zero_empty); break;
-                    case 2: put_lit(r, " + "); break;
-                    case 3: put_decimal(r, (uint64_t)data[(col * 4 + 1) * stride + row], zero_empty); break;
-                    case 4: put_lit(r, " * u) + QuadExtField("); break;
-                    case 5: put_decimal(r, (uint64_t)data[(col * 4 + 2) * stride + row], zero_empty); break;
-                    case 6: put_lit(r, " + "); break;
-                    case 7: put_decimal(r, (uint64_t)data[(col * 4 + 3) * stride + row], zero_empty); break;
-                    default: put_lit(r, " * u) * u)"); break;
+                    case 0: put_lit(st, "QuadExtField("); break;
+                    case 1: put_lit(st, "QuadExtField("); break;
+                    case 2: put_decimal(st, (uint64_t)data[(col * 4 + 0) * stride + row], zero_empty, dec4); break;
+                    case 3: put_lit(st, " + "); break;
+                    case 4: put_decimal(st, (uint64_t)data[(col * 4 + 1) * stride + row], zero_empty, dec4); break;
+                    case 5: put_lit(st, " * u) + "); break;
+                    case 6: put_lit(st, "QuadExtField("); break;
+                    case 7: put_decimal(st, (uint64_t)data[(col * 4 + 2) * stride + row], zero_empty, dec4); break;
+                    case 8: put_lit(st, " + "); break;
+                    case 9: put_decimal(st, (uint64_t)data[(col * 4 + 3) * stride + row], zero_empty, dec4); break;
+                    default: put_lit(st, " * u) * u)"); break;
                 }
             }
-            total_bytes += r.pos - before;
             tok++;
             if (++sub == Tokens<DEG>::PER_ELEM) {
                 sub = 0;
@@ -143,34 +186,43 @@ k_leaf_hash(const typename F::T* __restrict__ data, uint64_t stride, uint64_t wi
             }
         }
         // ---- padding once the message is complete (FIPS 180-4 5.1.1)
-        if (!padded && r.pos < 64 && tok >= ntok) {
-            r.put(0x80);
-            uint32_t end = (r.pos <= 56) ? 64u : 128u;  // bytes beyond are already zero
-            uint64_t bits = total_bytes * 8;
-            r.pos = end - 8;
-#pragma unroll
-            for (int i = 7; i >= 0; i--) r.put((uint32_t)(bits >> (8 * i)) & 0xffu);
+        if (!padded && st.wr < 16 && tok >= ntok) {
+            const uint64_t bits = st.total * 8;
+            const uint32_t one[1] = {0x80000000u};
+            st.append<1>(one, 1);
+            const uint32_t nw = st.wr + (st.fill ? 1u : 0u);  // words holding data
+            end_words = nw <= 14 ? 16u : 32u;
+            for (uint32_t i = nw; i < end_words - 2; i++) st.base[i * LEAF_THREADS] = 0;
+            st.base[(end_words - 2) * LEAF_THREADS] = (uint32_t)(bits >> 32);
+            st.base[(end_words - 1) * LEAF_THREADS] = (uint32_t)bits;
+            st.wr = end_words;
             padded = true;
         }
-        // ---- compress one pending block
-        if (!finished && r.pos >= 64) {
+        // ---- compress one pending block and slide the rest of the buffer down
+        if (!finished && st.wr >= 16) {
             uint32_t w[16];
-            const uint32_t wb = r.base >> 2;
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                w[i] = r.w[(wb + i) * LEAF_THREADS];
-                r.w[(wb + i) * LEAF_THREADS] = 0;
+            for (int i = 0; i < 16; i++) w[i] = st.base[i * LEAF_THREADS];
+            sha256_compress(h, w);
+            st.wr -= 16;
+            if (padded) {
+                if (st.wr == 0) finished = true;
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) st.base[i * LEAF_THREADS] = st.base[(i + 16) * LEAF_THREADS];
+                }
+            } else {
+                // at most 6 complete words plus the partial one were beyond the block
+#pragma unroll
+                for (int i = 0; i < 7; i++) st.base[i * LEAF_THREADS] = st.base[(i + 16) * LEAF_THREADS];
+                st.wp -= 16 * LEAF_THREADS;
             }
-            sha256_compress(st, w);
-            r.base ^= 64u;
-            r.pos -= 64;
-            if (padded && r.pos == 0) finished = true;
         }
     }
     if (live) {
         uint4* o = reinterpret_cast<uint4*>(nodes + g * 8);
-        o[0] = make_uint4(st[0], st[1], st[2], st[3]);
-        o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+        o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        o[1] = make_uint4(h[4], h[5], h[6], h[7]);
     }
 }
 
@@ -265,13 +317,24 @@ inline int merkle_reduce(Ctx* c, const uint32_t* d_digests, uint64_t n, uint64_t
     return MS_OK;
 }
 
+inline int ensure_dec4(Ctx* c) {
+    if (c->dec4) return MS_OK;
+    uint32_t* t;
+    MS_CUDA(c, cudaMalloc(&t, 10000 * sizeof(uint32_t)));
+    k_build_dec4<<<(10000 + 255) / 256, 256, 0, c->stream>>>(t);
+    MS_LAUNCH_CHECK(c);
+    c->dec4 = t;
+    return MS_OK;
+}
+
 template <class F>
 int merkle_leaf_level(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t width, int deg, uint64_t lpn, uint64_t n1,
                       uint32_t* d_nodes) {
     unsigned blocks = (unsigned)((n1 + LEAF_THREADS - 1) / LEAF_THREADS);
     prof_begin(c, "k_leaf_hash");
-    if (deg == 1) k_leaf_hash<F, 1><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
-    else k_leaf_hash<F, F::D><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, d_nodes);
+    MS_TRY(ensure_dec4(c));
+    if (deg == 1) k_leaf_hash<F, 1><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, c->dec4, d_nodes);
+    else k_leaf_hash<F, F::D><<<blocks, LEAF_THREADS, 0, c->stream>>>(d_data, stride, width, lpn, n1, c->zero_display_empty, c->dec4, d_nodes);
     prof_end(c);
     MS_LAUNCH_CHECK(c);
     return MS_OK;

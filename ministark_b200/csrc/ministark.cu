@@ -64,6 +64,7 @@ void ms_ctx_destroy(ms_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; i++)
         if (c->wtab[i]) cudaFree(c->wtab[i]);
+    if (c->dec4) cudaFree(c->dec4);
     delete c->prover;
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -107,6 +108,12 @@ int32_t ms_profile_collect(ms_ctx* c, const char** names, float* total_ms, uint3
 int32_t ms_set_zero_display(ms_ctx* c, int32_t empty) {
     c->zero_display_empty = empty ? 1 : 0;
     return MS_OK;
+}
+
+int32_t ms_selftest_field_ops(ms_ctx* c, uint64_t n_random, uint64_t* n_bad) {
+#define CALL(F) selftest_ops<F>(c, n_random, n_bad)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
 }
 
 int32_t ms_dev_alloc(ms_ctx* c, size_t bytes, void** d_out) {

@@ -822,6 +822,66 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     return MS_OK;
 }
 
+// Device self-test of the butterfly arithmetic against the canonical host ops (edge values first,
+// then xorshift-random operands): returns the number of mismatching (a, b) pairs.
+template <class F>
+__global__ void k_selftest_ops(const typename F::T* a, const typename F::T* b, typename F::T* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using A = Fast<F>;
+    typename F::T m = A::mul(a[i], A::to_tw(b[i]));
+    out[4 * i] = m;
+    out[4 * i + 1] = A::add(a[i], m);
+    out[4 * i + 2] = A::sub(a[i], m);
+    out[4 * i + 3] = A::canon(a[i]);
+}
+template <class F>
+int selftest_ops(Ctx* c, uint64_t n_random, uint64_t* n_bad) {
+    using T = typename F::T;
+    const uint64_t P = (uint64_t)F::P;
+    const bool lazy = sizeof(T) == 8;  // Goldilocks accepts any 64-bit representative; BabyBear operands are canonical
+    std::vector<uint64_t> edge = {0, 1, 2, P - 2, P - 1};
+    if (lazy) {
+        const uint64_t more[] = {P, P + 1, ~0ULL, ~0ULL - 1, 0xFFFFFFFFULL, 0x100000000ULL, 0xFFFFFFFF00000000ULL, 0xFFFFFFFEFFFFFFFFULL, 0x8000000000000000ULL};
+        for (uint64_t e : more) edge.push_back(e);
+    }
+    std::vector<T> a, b;
+    for (auto x : edge) for (auto y : edge) { a.push_back((T)x); b.push_back((T)(y % P)); }
+    uint64_t s = 88172645463325252ULL;
+    for (uint64_t i = 0; i < n_random; i++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17; uint64_t x = s;
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17; uint64_t y = s;
+        if (i % 7 == 0) x |= 0xFFFFFFFF00000000ULL;
+        if (i % 13 == 0) x &= 0xFFFFFFFFULL;
+        a.push_back(lazy ? (T)x : (T)(x % P));
+        b.push_back((T)(y % P));
+    }
+    const int n = (int)a.size();
+    Scratch da(c), db(c), dout(c);
+    MS_TRY(da.alloc(n * sizeof(T)));
+    MS_TRY(db.alloc(n * sizeof(T)));
+    MS_TRY(dout.alloc(4 * (size_t)n * sizeof(T)));
+    MS_CUDA(c, cudaMemcpyAsync(da.p, a.data(), n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaMemcpyAsync(db.p, b.data(), n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    k_selftest_ops<F><<<(n + 255) / 256, 256, 0, c->stream>>>(da.as<T>(), db.as<T>(), dout.as<T>(), n);
+    MS_LAUNCH_CHECK(c);
+    std::vector<T> out(4 * (size_t)n);
+    MS_CUDA(c, cudaMemcpyAsync(out.data(), dout.p, out.size() * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint64_t bad = 0;
+    for (int i = 0; i < n; i++) {
+        const uint64_t av = (uint64_t)a[i] % P, bv = (uint64_t)b[i];
+        const uint64_t m = (uint64_t)(((unsigned __int128)av * bv) % P);
+        const uint64_t ad = (uint64_t)(((unsigned __int128)av + m) % P), sb = (uint64_t)(((unsigned __int128)av + P - m) % P);
+        bool ok = (uint64_t)out[4 * i] == m && (uint64_t)out[4 * i + 1] % P == ad && (uint64_t)out[4 * i + 2] % P == sb &&
+                  (uint64_t)out[4 * i + 3] == av;
+        if (!lazy) ok = ok && (uint64_t)out[4 * i + 1] < P && (uint64_t)out[4 * i + 2] < P;
+        bad += ok ? 0 : 1;
+    }
+    if (n_bad) *n_bad = bad;
+    return MS_OK;
+}
+
 template <class F>
 int transpose(Ctx* c, const typename F::T* d_in, typename F::T* d_out, uint64_t rows, uint64_t width, bool to_colmajor) {
     if (rows == 0 || width == 0) return MS_OK;

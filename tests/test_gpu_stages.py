@@ -172,3 +172,14 @@ def test_merkle_large_property(ctxs, oracle):
         off += lv
         lv //= 2
     assert bytes(nb[-1]) == root
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+def test_butterfly_arithmetic_selftest(field, ctxs):
+    """Fast<F>::mul/add/sub/canon (lazy PTX carry chains / Montgomery twiddles) against exact host arithmetic,
+    edge representatives (0, p-1, p, 2^64-1, ...) and 2^20 random pairs."""
+    import ctypes as C
+
+    bad = C.c_uint64(123)
+    ctxs[field]._check(ctxs[field].lib.ms_selftest_field_ops(ctxs[field].h, 1 << 20, C.byref(bad)))
+    assert bad.value == 0
