@@ -17,6 +17,8 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
+    cudaStream_t copy_stream = nullptr;  // proof download (overlaps the query-phase kernels)
+    cudaEvent_t copy_event = nullptr;
     std::string err;
     int zero_display_empty = 0;  // ark-ff 0.4 printed "" for zero; 0.5.0 prints "0" 
     void* wtab[2] = {nullptr, nullptr};  // plain DIT twiddles, forward / inverse (see ntt.cuh)

@@ -49,6 +49,11 @@ int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out)
     // NULL = the legacy default stream (what torch uses unless told otherwise), so that the caller's
     // copies and this library's kernels are ordered without extra synchronisation
     c->stream = reinterpret_cast<cudaStream_t>(stream);
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return MS_ERR_CUDA;
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -65,6 +70,8 @@ void ms_ctx_destroy(ms_ctx* c) {
     for (int i = 0; i < 2; i++)
         if (c->wtab[i]) cudaFree(c->wtab[i]);
     if (c->dec4) cudaFree(c->dec4);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_event) cudaEventDestroy(c->copy_event);
     delete c->prover;
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;

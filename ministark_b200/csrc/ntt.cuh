@@ -70,6 +70,14 @@ MS_HD uint32_t brev_bits(uint32_t x, int bits) {
 template <class F>
 struct Fast;
 
+// 2^64 mod p = 2^32 - 1 kept in constant memory on purpose.  Measured on B200 (scratch/ubench/pipes.cu,
+// SM clocks per warp instruction per scheduler): IADD3 / LOP3 / IMAD 2.0, IMAD.WIDE 2.6, IMAD.HI 5.4.
+// With the literal 0xFFFFFFFF ptxas rewrites every "x * (2^32-1) + y" into IMAD.HI + IADD3 (7.4 clocks);
+// with an operand it cannot see through it stays one IMAD.WIDE (2.6 clocks).
+#ifdef __CUDACC__
+__constant__ uint32_t GL_EPS_OPAQUE = 0xFFFFFFFFu;
+#endif
+
 template <>
 struct Fast<GL> {
     using T = uint64_t;
@@ -79,10 +87,12 @@ struct Fast<GL> {
         // 128-bit product c3..c0, then c0 + c1 2^32 + c2 (2^32 - 1) - c3 with every carry folded
         // back once; the last fold also subtracts p when the sum landed in [p, 2^64).
         uint32_t r0, r1;
+        const uint32_t eps = GL_EPS_OPAQUE;
         asm("{\n\t"
             ".reg .u32 c0, c1, c2, c3, m, k, d;\n\t"
-            "mul.lo.u32 c0, %2, %4;\n\t"
-            "mul.hi.u32 c1, %2, %4;\n\t"
+            ".reg .u64 pp;\n\t"
+            "mul.wide.u32 pp, %2, %4;\n\t"
+            "mov.b64 {c0, c1}, pp;\n\t"
             "mad.lo.cc.u32 c1, %2, %5, c1;\n\t"
             "madc.hi.u32 c2, %2, %5, 0;\n\t"
             "mad.lo.cc.u32 c1, %3, %4, c1;\n\t"
@@ -95,17 +105,17 @@ struct Fast<GL> {
             "subc.u32 m, 0, 0;\n\t"
             "sub.cc.u32 c0, c0, m;\n\t"
             "subc.u32 c1, c1, 0;\n\t"
-            "mad.lo.cc.u32 c0, c2, 0xFFFFFFFF, c0;\n\t"
-            "madc.hi.cc.u32 c1, c2, 0xFFFFFFFF, c1;\n\t"
+            "mad.lo.cc.u32 c0, c2, %6, c0;\n\t"
+            "madc.hi.cc.u32 c1, c2, %6, c1;\n\t"
             "addc.u32 k, 0, 0;\n\t"
             "add.cc.u32 d, c0, 0xFFFFFFFF;\n\t"
             "addc.cc.u32 d, c1, 0;\n\t"
             "addc.u32 k, k, 0;\n\t"
-            "mad.lo.cc.u32 %0, k, 0xFFFFFFFF, c0;\n\t"
-            "madc.hi.u32 %1, k, 0xFFFFFFFF, c1;\n\t"
+            "mad.lo.cc.u32 %0, k, %6, c0;\n\t"
+            "madc.hi.u32 %1, k, %6, c1;\n\t"
             "}"
             : "=r"(r0), "=r"(r1)
-            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)), "r"(eps));
         return ((uint64_t)r1 << 32) | r0;
 #else
         return GL::mul(a % GL::P, b % GL::P);
@@ -114,14 +124,15 @@ struct Fast<GL> {
     static MS_HD T add(T a, T t) {
 #ifdef __CUDA_ARCH__
         uint32_t r0, r1;
+        const uint32_t eps = GL_EPS_OPAQUE;
         asm("{\n\t.reg .u32 k, s0, s1;\n\t"
             "add.cc.u32 s0, %2, %4;\n\t"
             "addc.cc.u32 s1, %3, %5;\n\t"
             "addc.u32 k, 0, 0;\n\t"
-            "mad.lo.cc.u32 %0, k, 0xFFFFFFFF, s0;\n\t"
-            "madc.hi.u32 %1, k, 0xFFFFFFFF, s1;\n\t}"
+            "mad.lo.cc.u32 %0, k, %6, s0;\n\t"
+            "madc.hi.u32 %1, k, %6, s1;\n\t}"
             : "=r"(r0), "=r"(r1)
-            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)t), "r"((uint32_t)(t >> 32)));
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)t), "r"((uint32_t)(t >> 32)), "r"(eps));
         return ((uint64_t)r1 << 32) | r0;
 #else
         T s = a + t;
@@ -153,10 +164,10 @@ struct Fast<GL> {
             "add.cc.u32 d, %2, 0xFFFFFFFF;\n\t"
             "addc.cc.u32 d, %3, 0;\n\t"
             "addc.u32 k, 0, 0;\n\t"
-            "mad.lo.cc.u32 %0, k, 0xFFFFFFFF, %2;\n\t"
-            "madc.hi.u32 %1, k, 0xFFFFFFFF, %3;\n\t}"
+            "mad.lo.cc.u32 %0, k, %4, %2;\n\t"
+            "madc.hi.u32 %1, k, %4, %3;\n\t}"
             : "=r"(r0), "=r"(r1)
-            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)));
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"(GL_EPS_OPAQUE));
         return ((uint64_t)r1 << 32) | r0;
 #else
         return a >= GL::P ? a - GL::P : a;

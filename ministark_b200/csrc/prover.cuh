@@ -389,12 +389,22 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             pw.u64(nq);
             if (nq) copies.push_back({pw.reserve(nq * sizeof(E)), d_quot + (size_t)k * nq * D, (size_t)(nq * sizeof(E))});
         }
+        // The quotient polynomials are ~all of the proof bytes (fri.rs:167): start this round's download on
+        // the copy stream now, so it overlaps the next rounds' kernels and host work (the proof buffer was
+        // checked against the size bound up front, so every offset is in range).
+        if (!copies.empty()) {
+            MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
+            MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
+            for (auto& cp : copies)
+                MS_CUDA(c, cudaMemcpyAsync(proof_out + cp.at, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            copies.clear();
+        }
     }
+    MS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     if (!pw.fits()) {
         *proof_len = pw.pos;
         return fail(c, MS_ERR_BUFFER_TOO_SMALL, "proof buffer needs %llu bytes", (unsigned long long)pw.pos);
     }
-    for (auto& cp : copies) MS_CUDA(c, cudaMemcpyAsync(proof_out + cp.at, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->stream));
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
     tm.end();
     *proof_len = pw.pos;

@@ -17,10 +17,13 @@ __host__ __device__ __forceinline__ uint32_t sha_rotr(uint32_t x, int n) {
 }
 
 // SHA-256 is all rotates, 3-input logic and adds: on sm_100a every one of those issues on the ALU
-// pipe (SHF / LOP3 / IADD3, one warp instruction per two cycles) while the FMA pipe idles.  A rotate
-// is also  hi(x * 2^(32-n)) + lo(x * 2^(32-n)),  i.e. IMAD.HI + IMAD on the FMA pipe.  The multiplier
-// is read from constant memory so that ptxas cannot strength-reduce it back into a shift.  Which
-// rotates take this route is a tuning mask (MS_SHA_FMA_MASK: 1 Sigma1, 2 Sigma0, 4 sigma0, 8 sigma1).
+// pipe (SHF / LOP3 / IADD3, one warp instruction per two cycles per scheduler) while the FMA pipe
+// idles; ncu shows the hashing kernels at ~90 % ALU-pipe utilisation.  A rotate is also the two halves
+// of the 64-bit product x * 2^(32-n): one IMAD.WIDE on the FMA pipe, and since the halves have
+// disjoint bits they can go straight into the 3-input XORs.  Per Sigma / sigma that trades
+// (3 SHF + 1 LOP3) for (2 IMAD.WIDE + 1 SHF + 2 LOP3): one ALU instruction less.  The multiplier is
+// read from constant memory so that ptxas cannot strength-reduce it back into shifts.
+// MS_SHA_FMA_MASK selects where this is applied: 1 Sigma1, 2 Sigma0, 4 sigma0, 8 sigma1.
 #ifndef MS_SHA_FMA_MASK
 #define MS_SHA_FMA_MASK 0
 #endif
@@ -30,15 +33,16 @@ __constant__ uint32_t SHA_ROT_MUL[32] = {
     1u << 21,  1u << 20, 1u << 19, 1u << 18, 1u << 17, 1u << 16, 1u << 15, 1u << 14, 1u << 13, 1u << 12, 1u << 11,
     1u << 10,  1u << 9,  1u << 8,  1u << 7,  1u << 6,  1u << 5,  1u << 4,  1u << 3,  1u << 2,  1u << 1};
 #endif
+// xor of rotr(x, n1), rotr(x, n2) and `third` (a rotate or a shift computed by the caller)
 template <int WHICH>
-__host__ __device__ __forceinline__ uint32_t sha_rot(uint32_t x, int n) {
+__host__ __device__ __forceinline__ uint32_t sha_xor3(uint32_t x, int n1, int n2, uint32_t third) {
 #ifdef __CUDA_ARCH__
     if (MS_SHA_FMA_MASK & WHICH) {
-        const uint32_t c = SHA_ROT_MUL[n];
-        return __umulhi(x, c) + x * c;
+        const uint64_t p1 = (uint64_t)x * SHA_ROT_MUL[n1], p2 = (uint64_t)x * SHA_ROT_MUL[n2];
+        return ((uint32_t)p1 ^ (uint32_t)(p1 >> 32) ^ (uint32_t)p2) ^ ((uint32_t)(p2 >> 32) ^ third);
     }
 #endif
-    return sha_rotr(x, n);
+    return sha_rotr(x, n1) ^ sha_rotr(x, n2) ^ third;
 }
 
 __host__ __device__ __forceinline__ void sha256_init(uint32_t st[8]) {
@@ -66,15 +70,15 @@ __host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_
             wi = w[i];
         } else {
             uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-            uint32_t s0 = sha_rot<4>(w15, 7) ^ sha_rot<4>(w15, 18) ^ (w15 >> 3);
-            uint32_t s1 = sha_rot<8>(w2, 17) ^ sha_rot<8>(w2, 19) ^ (w2 >> 10);
+            uint32_t s0 = sha_xor3<4>(w15, 7, 18, w15 >> 3);
+            uint32_t s1 = sha_xor3<8>(w2, 17, 19, w2 >> 10);
             wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
             w[i & 15] = wi;
         }
-        uint32_t S1 = sha_rot<1>(e, 6) ^ sha_rot<1>(e, 11) ^ sha_rot<1>(e, 25);
+        uint32_t S1 = sha_xor3<1>(e, 6, 11, sha_rotr(e, 25));
         uint32_t ch = (e & f) ^ (~e & g);
         uint32_t t1 = h + S1 + ch + K[i] + wi;
-        uint32_t S0 = sha_rot<2>(a, 2) ^ sha_rot<2>(a, 13) ^ sha_rot<2>(a, 22);
+        uint32_t S0 = sha_xor3<2>(a, 2, 13, sha_rotr(a, 22));
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
         uint32_t t2 = S0 + mj;
         h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;

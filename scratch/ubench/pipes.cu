@@ -1,0 +1,73 @@
+// Integer pipe throughput microbenchmark (run under ncu for exact instruction counts, or standalone).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#define ITERS 4096
+// NA chains of op A and NB chains of op B per thread, all independent
+template <int A, int NA, int B, int NB>
+__global__ void __launch_bounds__(512) k(uint32_t* out, uint32_t seed, long long* cycles) {
+    uint32_t x[16], y[16], z[16];
+    uint64_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { x[i] = seed + threadIdx.x * 7 + i; y[i] = seed * 3 + i * 13 + threadIdx.x; z[i] = y[i] ^ 0x5555; w[i] = x[i]; }
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int op = i < NA ? A : (i < NA + NB ? B : -1);
+            if (op == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+            if (op == 1) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+            if (op == 2) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(y[i]), "r"(z[i]));
+            if (op == 3) asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+            if (op == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+            if (op == 5) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+            if (op == 6) asm volatile("{add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;}" : "+r"(x[i]), "+r"(y[i]) : "r"(z[i]), "r"(seed));
+            if (op == 7) asm volatile("{mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;}" : "+r"(x[i]), "+r"(y[i]) : "r"(z[i]), "r"(seed));
+        }
+    }
+    long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc += x[i] + y[i] + (uint32_t)w[i] + (uint32_t)(w[i] >> 32);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+template <int A, int NA, int B, int NB>
+void run(const char* name) {
+    const int blocks = 148 * 2, threads = 512;
+    uint32_t* out; long long* cyc;
+    cudaMalloc(&out, blocks * threads * 4); cudaMalloc(&cyc, blocks * 8);
+    k<A, NA, B, NB><<<blocks, threads>>>(out, 12345, cyc);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k<A, NA, B, NB><<<blocks, threads>>>(out, 12345, cyc);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    long long h[296]; cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < blocks; i++) avg += h[i]; avg /= blocks;
+    double ops = 32.0 * ITERS * (NA + NB);  // PTX-level ops per SM (32 warps)
+    printf("%-26s %8.0f cyc %.3f ms => clock64 %.0f MHz | %.2f ops/clk/SM (%.2f clk/op/SMSP)\n", name, avg, ms, avg / ms / 1e3, ops / avg, avg / (8.0 * ITERS * (NA + NB)));
+    cudaFree(out); cudaFree(cyc);
+}
+int main() {
+    run<0, 16, 0, 0>("IMAD x16");
+    run<1, 16, 0, 0>("IMAD.HI x16");
+    run<2, 16, 0, 0>("IMAD.WIDE x16");
+    run<3, 16, 0, 0>("IADD3(3-input) x16");
+    run<4, 16, 0, 0>("LOP3 x16");
+    run<5, 16, 0, 0>("SHF x16");
+    run<6, 16, 0, 0>("add.cc+addc x16 (2 inst)");
+    run<7, 16, 0, 0>("mad.lo.cc+madc.hi x16");
+    run<2, 8, 3, 8>("IMAD.WIDE x8 + IADD3 x8");
+    run<2, 8, 4, 8>("IMAD.WIDE x8 + LOP3 x8");
+    run<0, 8, 3, 8>("IMAD x8 + IADD3 x8");
+    run<3, 8, 4, 8>("IADD3 x8 + LOP3 x8");
+    run<2, 4, 3, 12>("IMAD.WIDE x4 + IADD3 x12");
+    run<2, 5, 4, 10>("IMAD.WIDE x5 + LOP3 x10");
+    run<1, 4, 3, 12>("IMAD.HI x4 + IADD3 x12");
+    run<5, 8, 4, 8>("SHF x8 + LOP3 x8");
+    return 0;
+}

@@ -145,7 +145,7 @@ static int check(int logN, int logB, bool inverse, int force_a, uint64_t cols) {
     T scale = inverse ? finv<F>((T)(N % (uint64_t)F::P)) : (T)1;
     int bad = 0;
     for (uint64_t c = 0; c < cols; c++)
-        for (uint64_t i = 0; i < L; i += (L > 256 ? 37 : 1)) {
+        for (uint64_t i = 0; i < L; i += (L > 256 ? (L > 4096 ? L / 24 + 1 : 37) : 1)) {
             T x = F::mul(shift, fpow<F>(wL, i)), acc = 0;
             for (uint64_t m = N; m-- > 0;) acc = F::add(F::mul(acc, x), in[c * N + m]);
             acc = F::mul(acc, scale);

@@ -1,0 +1,114 @@
+"""CPU-only checks of the drop-in boundary: libministark.so loads without a GPU, exports every symbol
+include/ministark.h declares (and nothing is declared that the ctypes binding does not know), the
+host-side parameter derivation (StarkConfig::new, src/starks.rs:268-332) answers without a device, the
+host mirror of the reference API behaves like src/air.rs, and the product never reaches into oracle/."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "ministark.h")) as fh:
+        text = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(ms_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ministark_b200 import _lib
+    from ministark_b200 import build as b
+
+    b.build()
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ministark.h but not exported"
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert lib.ms_version() >= 1
+
+
+def test_no_compute_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    from ministark_b200 import Context, MiniStarkError
+
+    with pytest.raises(MiniStarkError):
+        Context(0)  # no CPU fallback
+
+
+@pytest.mark.parametrize("field,args,want", [
+    (0, (20, 4, 129), (1, 3)), (0, (128, 4, 129), (3, 19)), (0, (256, 4, 513), (5, 32)),  # src/starks.rs:348-374
+])
+def test_stark_derive_matches_reference_unit_tests(field, args, want, pyref):
+    from ministark_b200 import _lib
+
+    lib = _lib.load()
+    sec, blow, steps = args
+    p = _lib.StarkParams(sec, blow, steps, 6, 2)
+    r, q, fq = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert lib.ms_stark_derive(field, C.byref(p), C.byref(r), C.byref(q), C.byref(fq)) == 0
+    assert (q.value, fq.value) == want
+    cfg = pyref.StarkConfig(pyref.FIELDS[field], sec, blow, steps, 6)
+    assert (r.value, q.value, fq.value) == (cfg.rounds, cfg.constrain_queries, cfg.fri_config.queries)
+
+
+def test_stark_derive_rejects_low_security():
+    from ministark_b200 import _lib
+
+    lib = _lib.load()
+    p = _lib.StarkParams(19, 4, 9, 6, 2)  # starks.rs:317-320 panics below 20 bits
+    assert lib.ms_stark_derive(0, C.byref(p), None, None, None) != 0
+
+
+def test_merkle_node_count_matches_reference_unit_tests():
+    from ministark_b200 import _lib
+
+    lib = _lib.load()
+    # merkle.rs:399-419: 16 leaves with (lpn, k) = (2,2),(4,2),(4,4),(16,16) -> 31/23/21/17 nodes incl. leaves;
+    # the digest count is that minus the 16 raw leaves
+    for lpn, k, total in ((2, 2, 31), (4, 2, 23), (4, 4, 21), (16, 16, 17)):
+        assert lib.ms_merkle_node_count(16 // lpn, k) == total - 16
+    assert lib.ms_merkle_node_count(8, 4) == 0  # not full (merkle.rs:384-396 panics)
+
+
+def test_trace_table_mirror_matches_air_rs(pyref):
+    """air.rs:245-300: padded sizes 3->4, 4->8, 5->8 rows; padding cells equal and non-zero; linear matrix
+    of the e2e AIR's closures."""
+    from ministark_b200.air import DensePolynomial, TraceTable
+    from ministark_b200.field import FIELDS
+
+    F = FIELDS[0]
+    for steps, rows in ((3, 4), (4, 8), (5, 8), (9, 16)):
+        t = TraceTable(F, steps, 3)
+        assert t.data.shape == (rows, 3)
+        pad = t.data[steps:]
+        assert (pad == pad[0, 0]).all() and int(pad[0, 0]) != 0
+        rt = pyref.TraceTable(pyref.FIELDS[0], steps, 3)
+        assert [int(v) for v in t.data.reshape(-1)] == rt.data
+    t = TraceTable(F, 9, 3)
+    om = DensePolynomial(F, [t.omega])
+    t.add_transition_constrain(lambda P: P[0].clone() * om - P[1].clone())
+    t.add_transition_constrain(lambda P: P[2].clone() - P[0].clone() - P[1].clone())
+    m = t.linear_matrix()
+    p = F.p
+    assert m.tolist() == [[t.omega, p - 1, 0], [p - 1, p - 1, 1]]
+    assert t.constrain_number() == 5
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "ministark_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    src = fh.read()
+                code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("#", "//", "*", '"""')))
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", code, flags=re.M), f
+                assert "liboracle" not in code, f
