@@ -183,6 +183,11 @@ typedef struct ms_commit_hooks {
     int32_t (*trace_commit)(void* user, const void* d_trace_colmajor, uint64_t n, uint64_t w, uint8_t* root32);
     int32_t (*lde_commit)(void* user, const void* d_coeffs_colmajor, uint64_t n, uint64_t cols, uint64_t blowup,
                           uint64_t shift, uint8_t* root32);
+    /* non-zero on ranks whose proof bytes nobody reads (every rank but one): all stages still run, so the
+     * transcript and the device state stay in lock step, but the per-query quotient polynomials -- ~all of
+     * the proof bytes, src/fri.rs:167 -- are not downloaded (N simultaneous multi-GB PCIe reads would
+     * only slow rank 0 down).  proof_out then holds the fixed part and *proof_len the full length. */
+    int32_t replica_only;
 } ms_commit_hooks;
 /* ms_stark_prove_device with the two commitments routed through `hooks` (NULL members = local). */
 int32_t ms_stark_prove_hooked(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,

@@ -31,7 +31,8 @@ LDE_COMMIT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_u
 
 class CommitHooks(C.Structure):
     """ms_commit_hooks (include/ministark.h)"""
-    _fields_ = [("user", C.c_void_p), ("trace_commit", TRACE_COMMIT_FN), ("lde_commit", LDE_COMMIT_FN)]
+    _fields_ = [("user", C.c_void_p), ("trace_commit", TRACE_COMMIT_FN), ("lde_commit", LDE_COMMIT_FN),
+                ("replica_only", C.c_int32)]
 
 
 # every symbol include/ministark.h declares: name -> (restype, argtypes)

@@ -245,12 +245,7 @@ k_node_hash(const uint32_t* __restrict__ children, uint32_t* __restrict__ parent
         }
         sha256_compress(st, w);
     }
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = 0;
-    w[0] = 0x80000000u;
-    w[15] = 32u * K * 8u;
-    sha256_compress(st, w);
+    sha256_compress_padblock<32u * K * 8u>(st);
     uint4* o = reinterpret_cast<uint4*>(parents + p * 8);
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);

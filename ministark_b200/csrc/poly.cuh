@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "field.cuh"
+#include "ntt.cuh"
 
 namespace ms {
 
@@ -125,8 +126,21 @@ k_eval_partial(const typename F::T* __restrict__ coef, uint64_t stride, uint64_t
     for (int q = 0; q < Q; q++) {
         const Ext<F>* tq = tab + (uint64_t)q * per_q;
         Ext<F> acc = cf[0];
+        if (CD == 1 && sizeof(typename F::T) == 8) {
+            // base coefficient x extension power, Goldilocks: lazy multiply-accumulate per coordinate
+            // (Fast<GL>: 17 + 5 instructions instead of 33 + 10 for the canonical ops)
 #pragma unroll
-        for (int k = 1; k < EV_SEG; k++) acc = ext_add(acc, coef_times<F, CD>(cf[k], tq[EV_THREADS + k]));
+            for (int k = 1; k < EV_SEG; k++) {
+                const Ext<F> pw = tq[EV_THREADS + k];
+#pragma unroll
+                for (int d = 0; d < F::D; d++) acc.c[d] = Fast<F>::add(acc.c[d], Fast<F>::mul(cf[k].c[0], pw.c[d]));
+            }
+#pragma unroll
+            for (int d = 0; d < F::D; d++) acc.c[d] = Fast<F>::canon(acc.c[d]);
+        } else {
+#pragma unroll
+            for (int k = 1; k < EV_SEG; k++) acc = ext_add(acc, coef_times<F, CD>(cf[k], tq[EV_THREADS + k]));
+        }
         acc = ext_mul(acc, tq[threadIdx.x]);
         // block sum: warp shuffles, then one value per warp through shared memory
 #pragma unroll

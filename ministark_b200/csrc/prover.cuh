@@ -392,6 +392,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         // The quotient polynomials are ~all of the proof bytes (fri.rs:167): start this round's download on
         // the copy stream now, so it overlaps the next rounds' kernels and host work (the proof buffer was
         // checked against the size bound up front, so every offset is in range).
+        if (hooks && hooks->replica_only) copies.clear();
         if (!copies.empty()) {
             MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
             MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));

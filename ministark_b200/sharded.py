@@ -223,7 +223,7 @@ class ShardedCommitter:
         return self.dist.get_global_rank(self.group, group_rank)
 
     # ---- ctypes glue
-    def hooks(self) -> "_lib.CommitHooks":
+    def hooks(self, replica_only: bool = False) -> "_lib.CommitHooks":
         def _tc(_user, d_trace, n, w, root32):
             try:
                 root = self.trace_commit(int(d_trace), int(n), int(w))
@@ -244,20 +244,21 @@ class ShardedCommitter:
 
         self.error: Optional[Exception] = None
         self._cb = (_lib.TRACE_COMMIT_FN(_tc), _lib.LDE_COMMIT_FN(_lc))
-        return _lib.CommitHooks(None, self._cb[0], self._cb[1])
+        return _lib.CommitHooks(None, self._cb[0], self._cb[1], 1 if replica_only else 0)
 
 
-def stark_prove_sharded(ctx, params, trace_cm, constraint_matrix: np.ndarray, out: np.ndarray, dist=None, group=None) -> int:
+def stark_prove_sharded(ctx, params, trace_cm, constraint_matrix: np.ndarray, out: np.ndarray, dist=None, group=None,
+                        proof_on_all_ranks: bool = False) -> int:
     """Stark::prove on this rank's replica with the commitments sharded over the process group.
-    trace_cm: device [W, N] (every rank holds it); out: host uint8 buffer.  Returns the proof length;
-    all ranks produce the same bytes."""
+    trace_cm: device [W, N] (every rank holds it); out: host uint8 buffer.  Returns the proof length.
+    Rank 0 holds the proof; with proof_on_all_ranks every rank downloads the (identical) bytes."""
     w, n = trace_cm.shape
     m = np.ascontiguousarray(constraint_matrix, dtype=ctx.np_dtype).reshape(-1, w)
     ops = getattr(ctx, "_sharded_ops", None)
     if ops is None:
         ops = ctx._sharded_ops = CudaOps(ctx)
     com = ShardedCommitter(ops, int(params.trace_columns), int(params.inner_children) or 2, dist, group)
-    hooks = com.hooks()
+    hooks = com.hooks(replica_only=(com.rank != 0 and not proof_on_all_ranks))
     cap = C.c_uint64(out.size)
     rc = ctx.lib.ms_stark_prove_hooked(ctx.h, C.byref(params), C.c_void_p(trace_cm.data_ptr()), n, w, m.ctypes.data, m.shape[0],
                                        C.byref(hooks), out.ctypes.data, C.byref(cap))

@@ -208,7 +208,7 @@ def _nccl_worker(rank, world, port, log_n, w, blowup, k, q):
         m = synth_linear_matrix(0, n, w)
         params = StarkParams(40, blowup, n - 1, 2 * w, k)
         out = np.empty(int(ctx.lib.ms_stark_proof_bound(0, params, n, 2 * w)), dtype=np.uint8)
-        ln = stark_prove_sharded(ctx, params, ctx.to_device(np.ascontiguousarray(trace.T)), m, out, dist)
+        ln = stark_prove_sharded(ctx, params, ctx.to_device(np.ascontiguousarray(trace.T)), m, out, dist, proof_on_all_ranks=True)
         q.put((rank, hashlib.sha256(out[:ln].tobytes()).hexdigest()))
         ctx.close()
     finally:
