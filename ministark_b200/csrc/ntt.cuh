@@ -276,6 +276,7 @@ struct NttTile {
     int mode;             // 0: first (or only) pass, 1: second pass
     int plain;            // tw is the plain table (no coset factors): twiddles with q = 0 are exactly 1
     int bq;               // mode 0: log2(n1), the input stride of one transform step
+    int cs;               // mode 0: coset-split bits: tile = (m1 << cs) | sub, coset j = (sub << beta) | b (then R = 1)
     int a1, beta1, logR1; // mode 1: geometry of the first pass (a1 = log2 n2)
     uint32_t tiles;       // tiles per column
     uint32_t cols;
@@ -285,22 +286,32 @@ struct NttTile {
 template <class F>
 MS_HD uint64_t tile_src_index(const NttTile<F>& g, uint32_t tile, uint32_t P, uint32_t b) {
     if (g.mode == 0) {
+        if (g.cs) return (uint64_t)(tile >> g.cs) + ((uint64_t)brev_bits(P, g.a) << g.bq);
         const int logR = g.beta - g.logB;
         return ((uint64_t)tile << logR) + (b >> g.logB) + ((uint64_t)brev_bits(P, g.a) << g.bq);
     }
-    const int logR2 = g.beta - g.logB;
+    // second pass: the tile owns 2^beta consecutive lanes (k2, j) of the intermediate
     const uint64_t m1 = brev_bits(P, g.a);
-    const uint64_t k2 = ((uint64_t)tile << logR2) + (b >> g.logB);
-    const uint32_t j = b & ((1u << g.logB) - 1);
+    const uint64_t lane = ((uint64_t)tile << g.beta) + b;
+    const uint64_t k2 = lane >> g.logB;
+    const uint32_t j = (uint32_t)lane & ((1u << g.logB) - 1);
     return (((((m1 >> g.logR1) << g.a1) + k2) << g.beta1) | ((m1 & ((1u << g.logR1) - 1)) << g.logB)) + j;
 }
 template <class F>
 MS_HD uint64_t tile_dst_index(const NttTile<F>& g, uint32_t tile, uint32_t P, uint32_t b) {
-    if (g.mode == 0) return ((((uint64_t)tile << g.a) + P) << g.beta) | b;
-    const int logR2 = g.beta - g.logB;
-    const uint64_t k2 = ((uint64_t)tile << logR2) + (b >> g.logB);
-    const uint32_t j = b & ((1u << g.logB) - 1);
-    return ((((uint64_t)P << g.a1) + k2) << g.logB) | j;
+    if (g.mode == 0) {
+        if (g.cs) {
+            const uint32_t j = ((tile & ((1u << g.cs) - 1)) << g.beta) | b;
+            return (((((uint64_t)(tile >> g.cs)) << g.a) + P) << g.logB) | j;
+        }
+        return ((((uint64_t)tile << g.a) + P) << g.beta) | b;
+    }
+    return ((uint64_t)P << (g.a1 + g.logB)) + ((uint64_t)tile << g.beta) + b;
+}
+// coset of batch entry b (selects the twiddle table of a first-pass tile)
+template <class F>
+MS_HD uint32_t tile_coset(const NttTile<F>& g, uint32_t tile, uint32_t b) {
+    return g.cs ? (((tile & ((1u << g.cs) - 1)) << g.beta) | b) : b;
 }
 
 // shared-memory swizzle: bijection on every aligned group of 2^(2*SW) elements; makes the strided
@@ -328,7 +339,7 @@ MS_HD void tile_slot(const NttTile<F>& g, typename F::T* S, const typename F::T*
     const uint32_t b = slot & ((1u << g.beta) - 1), t = slot >> g.beta;
     const uint32_t lo = t & ((1u << u) - 1), hi = t >> u;
     const uint32_t P0 = lo + (hi << (u + G));
-    const T* __restrict__ twj = g.tw + (size_t)(b & g.jmask) * g.jstride + lo;
+    const T* __restrict__ twj = g.tw + (size_t)(tile_coset<F>(g, tile, b) & g.jmask) * g.jstride + lo;
     T w[E];  // w[2^s' + r'] = twiddle of local stage s', local index r'
 #pragma unroll
     for (int s = 0; s < G; s++)
@@ -479,7 +490,7 @@ MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::
         const uint32_t b = s & ((1u << BETA) - 1), t = s >> BETA;
         const uint32_t lo = t & ((1u << U) - 1), hi = t >> U;
         const uint32_t P0 = lo | (hi << (U + G));
-        const T* __restrict__ twj = g.tw + (size_t)(b & g.jmask) * g.jstride + lo;
+        const T* __restrict__ twj = g.tw + (size_t)(tile_coset<F>(g, tile, b) & g.jmask) * g.jstride + lo;
         T w[E];
 #pragma unroll
         for (int st = 0; st < G; st++)
@@ -492,11 +503,12 @@ MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::
             const T* p;
             uint32_t stride;  // elements between brev_G(r) = 1 and 2
             if (g.mode == 0) {
-                p = src + ((uint64_t)tile << logR) + (b >> g.logB) + ((uint64_t)m0 << g.bq);
+                p = src + (g.cs ? (uint64_t)(tile >> g.cs) : ((uint64_t)tile << logR) + (b >> g.logB)) + ((uint64_t)m0 << g.bq);
                 stride = 1u << (A - G + g.bq);
             } else {
-                const uint64_t k2 = ((uint64_t)tile << logR) + (b >> g.logB);
-                const uint32_t j = b & ((1u << g.logB) - 1);
+                const uint64_t lane = ((uint64_t)tile << BETA) + b;
+                const uint64_t k2 = lane >> g.logB;
+                const uint32_t j = (uint32_t)lane & ((1u << g.logB) - 1);
                 p = src + ((((((uint64_t)m0 >> g.logR1) << g.a1) + k2) << g.beta1) | ((m0 & ((1u << g.logR1) - 1)) << g.logB)) + j;
                 stride = 1u << (A - G - g.logR1 + g.a1 + g.beta1);
             }
@@ -544,12 +556,10 @@ MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::
             uint64_t o;
             uint32_t stride;
             if (g.mode == 0) {
-                o = ((((uint64_t)tile << A) + P0) << BETA) | b;
-                stride = 1u << (U + BETA);
+                o = tile_dst_index<F>(g, tile, P0, b);
+                stride = 1u << (U + (g.cs ? g.logB : BETA));
             } else {
-                const uint64_t k2 = ((uint64_t)tile << logR) + (b >> g.logB);
-                const uint32_t j = b & ((1u << g.logB) - 1);
-                o = ((((uint64_t)P0 << g.a1) + k2) << g.logB) | j;
+                o = ((uint64_t)P0 << (g.a1 + g.logB)) + ((uint64_t)tile << BETA) + b;
                 stride = 1u << (U + g.a1 + g.logB);
             }
             T* q = dst + o;
@@ -659,28 +669,40 @@ int ensure_wtab(Ctx* c, int inverse) {
 #endif
 
 struct NttPlan {
-    int a, b;        // N = 2^(a+b): pass 1 transforms 2^a points (stride 2^b), pass 2 2^b points
-    int logR1, logR2;  // extra batch per tile: consecutive m1 (pass 1) / consecutive k2 (pass 2)
+    int a, b;          // N = 2^(a+b): pass 1 transforms 2^a points (stride 2^b), pass 2 2^b points
+    int beta1, beta2;  // batch bits of a pass-1 / pass-2 tile
+    int logR1;         // pass 1: consecutive m1 per tile (beta1 = logR1 + logB) ...
+    int cs1;           // ... or, when 2^a points x B cosets exceed a tile, cosets split over 2^cs1 tiles
 };
+// Tiles hold 2^NTT_LOG_TILE_PREF elements.  Pass 1 batches extra m1 when the cosets do not fill a tile and
+// splits the cosets over several tiles when they overflow it; pass 2 takes whatever number of consecutive
+// (k2, coset) lanes fills a tile (fewer than B lanes for the largest transforms).
 inline bool ntt_plan(int logN, int logB, NttPlan* p) {
-    if (logN + logB <= NTT_LOG_TILE_PREF) {
-        *p = {logN, 0, 0, 0};
+    const int T = NTT_LOG_TILE_PREF;
+    if (logN + logB <= T) {
+        *p = {logN, 0, logB, 0, 0, 0};
         return true;
     }
     int a = (logN + 1) / 2, b = logN - a;
-    if (a + logB > NTT_LOG_TILE_MAX) {  // large blowup: shift stages into the second pass
-        a = NTT_LOG_TILE_MAX - logB;
-        if (a < 1) return false;
-        b = logN - a;
+    if (a > T || b > T) return false;
+    NttPlan pl{};
+    pl.a = a;
+    pl.b = b;
+    if (a + logB <= T) {
+        int r1 = T - a - logB;
+        if (r1 > b) r1 = b;
+        pl.logR1 = r1;
+        pl.beta1 = r1 + logB;
+        pl.cs1 = 0;
+    } else {
+        pl.cs1 = a + logB - T;
+        if (pl.cs1 > logB) return false;
+        pl.logR1 = 0;
+        pl.beta1 = logB - pl.cs1;
     }
-    if (b + logB > NTT_LOG_TILE_MAX) return false;
-    int r1 = NTT_LOG_TILE_PREF - a - logB;
-    if (r1 < 0) r1 = 0;
-    if (r1 > b) r1 = b;
-    int r2 = NTT_LOG_TILE_PREF - b - logB;
-    if (r2 < 0) r2 = 0;
-    if (r2 > a) r2 = a;
-    *p = {a, b, r1, r2};
+    pl.beta2 = T - b;
+    if (pl.beta2 > a + logB) pl.beta2 = a + logB;
+    *p = pl;
     return true;
 }
 
@@ -701,7 +723,7 @@ int launch_fixed(Ctx* c, const NttTile<F>& g, const char* name) {
 }
 
 // tile shapes with a compile-time specialisation
-#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2) X(11, 3)
+#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0)
 
 template <class F>
 int launch_tile(Ctx* c, const NttTile<F>& g, const char* name) {
@@ -773,6 +795,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         d_tw1 = t1.as<T>();
     }
     const bool inplace = two && pl.logR1 == 0 && tile_rounds(pl.b) >= 2;
+    const int lay1 = pl.logR1 + logB;  // low index bits (m1 offset, coset) of the intermediate layout
     if (two) {
         if (plain) {  // the shifts are still needed by k_build_ft
             MS_TRY(consts.alloc(hbuf.size() * sizeof(T)));
@@ -799,14 +822,15 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     g1.scale = Fast<F>::to_tw(scale);
     g1.has_scale = (!two && scale != 1) ? 1 : 0;
     g1.a = pl.a;
-    g1.beta = pl.logR1 + logB;
+    g1.beta = pl.beta1;
+    g1.cs = pl.cs1;
     g1.logB = logB;
     g1.jmask = plain ? 0u : (uint32_t)(B - 1);
     g1.jstride = plain ? 0u : (1u << pl.a);
     g1.mode = 0;
     g1.plain = plain ? 1 : 0;
     g1.bq = pl.b;
-    g1.tiles = (uint32_t)((1ULL << pl.b) >> pl.logR1);
+    g1.tiles = (uint32_t)(((1ULL << pl.b) >> pl.logR1) << pl.cs1);
     g1.cols = (uint32_t)cols;
     MS_TRY(launch_tile<F>(c, g1, "k_ntt_tile/pass1"));
     if (two) {
@@ -820,16 +844,16 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         g2.scale = 0;
         g2.has_scale = 0;
         g2.a = pl.b;
-        g2.beta = pl.logR2 + logB;
+        g2.beta = pl.beta2;
         g2.logB = logB;
         g2.jmask = 0;
         g2.jstride = 0;
         g2.mode = 1;
         g2.plain = 1;
         g2.a1 = pl.a;
-        g2.beta1 = g1.beta;
+        g2.beta1 = lay1;
         g2.logR1 = pl.logR1;
-        g2.tiles = (uint32_t)((1ULL << pl.a) >> pl.logR2);
+        g2.tiles = (uint32_t)(((1ULL << pl.a) << logB) >> pl.beta2);
         g2.cols = (uint32_t)cols;
         MS_TRY(launch_tile<F>(c, g2, "k_ntt_tile/pass2"));
     }

@@ -53,7 +53,7 @@ template <class F>
 static void run_any(const NttTile<F>& g) {
     if (g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0)) {
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) { g_fixed_used++; return run_fixed<F, A_, B_>(g); }
-        X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2) X(11, 3) X(5, 2) X(6, 0) X(7, 3)
+        X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(5, 2) X(6, 0) X(7, 3) X(5, 1) X(7, 1)
 #undef X
     }
     run_tiles<F>(g, 64);
@@ -68,9 +68,11 @@ static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, 
     if (!ntt_plan(logN, logB, &pl)) { printf("plan failed\n"); exit(2); }
     if (force_a >= 0) {  // exercise two-pass geometry on small sizes
         pl.a = force_a; pl.b = logN - force_a;
-        pl.logR1 = 0; pl.logR2 = 0;
-        if (logB == 0 && pl.b >= 2) pl.logR1 = 2;
-        if (logB == 0 && pl.a >= 1) pl.logR2 = 1;
+        pl.logR1 = 0; pl.cs1 = 0; pl.beta1 = logB; pl.beta2 = logB;
+        if (logB == 0 && pl.b >= 2) { pl.logR1 = 2; pl.beta1 = 2; }
+        if (logB == 0 && pl.a >= 1) pl.beta2 = 1;
+        if (logB == 2 && (force_a & 1)) { pl.cs1 = 1; pl.beta1 = 1; pl.beta2 = 1; }   // cosets split over two tiles, half-width pass 2
+        if (logB == 2 && force_a == 3) pl.beta2 = 0;
     }
     const int B = 1 << logB;
     const uint64_t N = 1ULL << logN;
@@ -115,16 +117,16 @@ static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, 
     g1.dst_stride = N << logB;
     g1.tw = t1.data(); g1.ft = two ? ft.data() : nullptr;
     g1.scale = Fast<F>::to_tw(scale); g1.has_scale = (!two && scale != 1) ? 1 : 0;
-    g1.a = pl.a; g1.beta = pl.logR1 + logB; g1.logB = logB;
+    g1.a = pl.a; g1.beta = pl.beta1; g1.cs = pl.cs1; g1.logB = logB;
     g1.jmask = B - 1; g1.jstride = 1u << pl.a; g1.mode = 0; g1.bq = pl.b;
-    g1.tiles = (uint32_t)((1ULL << pl.b) >> pl.logR1); g1.cols = (uint32_t)cols;
+    g1.tiles = (uint32_t)(((1ULL << pl.b) >> pl.logR1) << pl.cs1); g1.cols = (uint32_t)cols;
     run_any<F>(g1);
     if (two) {
         NttTile<F> g2{};
         g2.src = g1.dst; g2.src_stride = g1.dst_stride; g2.dst = out.data(); g2.dst_stride = N << logB;
-        g2.tw = wtab.data(); g2.a = pl.b; g2.beta = pl.logR2 + logB; g2.logB = logB; g2.mode = 1; g2.plain = 1;
-        g2.a1 = pl.a; g2.beta1 = g1.beta; g2.logR1 = pl.logR1;
-        g2.tiles = (uint32_t)((1ULL << pl.a) >> pl.logR2); g2.cols = (uint32_t)cols;
+        g2.tw = wtab.data(); g2.a = pl.b; g2.beta = pl.beta2; g2.logB = logB; g2.mode = 1; g2.plain = 1;
+        g2.a1 = pl.a; g2.beta1 = pl.logR1 + logB; g2.logR1 = pl.logR1;
+        g2.tiles = (uint32_t)(((1ULL << pl.a) << logB) >> pl.beta2); g2.cols = (uint32_t)cols;
         run_any<F>(g2);
     }
     return out;
@@ -184,6 +186,9 @@ int main() {
     bad += check<BB>(12, 0, false, 6, 1);
     bad += check<GL>(10, 3, false, 7, 1);    // (7,3)
     bad += check<GL>(12, 2, false, -1, 1);   // real two-pass plan
+    bad += check<GL>(12, 2, false, 7, 1);    // (7,1): cosets split over two tiles + (5,1) second pass
+    bad += check<BB>(12, 2, false, 7, 1);
+    bad += check<GL>(23, 2, false, -1, 1);   // planner's own coset split: (12,1) + (11,2)
     bad += check<GL>(14, 0, true, -1, 1);
     printf("fixed-shape tiles used: %d\n", g_fixed_used);
     printf(bad ? "FAILED\n" : "ALL OK\n");
