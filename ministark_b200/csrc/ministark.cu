@@ -17,19 +17,66 @@ struct ms_ctx : public ms::Ctx {
 #define FIELD_DISPATCH(ctx, CALL)                                            \
     ((ctx)->field == MS_FIELD_GOLDILOCKS ? CALL(ms::GL) : CALL(ms::BB))
 
+// Host-buffer LDE (the reference-facing call: coefficients in, row-major Matrix out, src/starks.rs:87-91).
+// PCIe is the bound (N*C*s in, L*C*s out), so the copies are pipelined against the kernels on the
+// context's copy stream: column groups are extended while the next group uploads, and the row-major
+// result leaves in row chunks through two staging buffers while the next chunk is transposed.
 template <class F>
 static int coset_lde_host(Ctx* c, const void* coeffs_host, uint64_t n, uint64_t cols, uint64_t blowup, uint64_t shift,
                           void* out_rm_host) {
     using T = typename F::T;
     const uint64_t L = n * blowup;
-    Scratch din(c), dout(c), drm(c);
+    if (n == 0 || cols == 0) return MS_OK;
+    const uint64_t ngroups = (n * cols * sizeof(T) >= (64u << 20)) ? (cols < 8 ? cols : 8) : 1;
+    const uint64_t nchunks = (L * cols * sizeof(T) >= (256u << 20) && L >= 1024) ? 16 : 1;
+    const uint64_t chunk_rows = (L + nchunks - 1) / nchunks;
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (auto e : v) cudaEventDestroy(e); }
+        cudaEvent_t make() {
+            cudaEvent_t e = nullptr;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            v.push_back(e);
+            return e;
+        }
+    } events;
+    Scratch din(c), dout(c), stage0(c), stage1(c);
     MS_TRY(din.alloc(n * cols * sizeof(T)));
     MS_TRY(dout.alloc(L * cols * sizeof(T)));
-    MS_TRY(drm.alloc(L * cols * sizeof(T)));
-    MS_CUDA(c, cudaMemcpyAsync(din.p, coeffs_host, n * cols * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-    MS_TRY(lde_batch<F>(c, din.as<T>(), n, cols, ilog2(n), ilog2(blowup), (T)(shift % (uint64_t)F::P), false, dout.as<T>(), L));
-    MS_TRY(transpose<F>(c, dout.as<T>(), drm.as<T>(), L, cols, false));
-    MS_CUDA(c, cudaMemcpyAsync(out_rm_host, drm.p, L * cols * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    MS_TRY(stage0.alloc(chunk_rows * cols * sizeof(T)));
+    MS_TRY(stage1.alloc(chunk_rows * cols * sizeof(T)));
+    cudaEvent_t ready = events.make();
+    MS_CUDA(c, cudaEventRecord(ready, c->stream));
+    MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, ready, 0));
+    const T* h_in = static_cast<const T*>(coeffs_host);
+    T* h_out = static_cast<T*>(out_rm_host);
+    for (uint64_t g = 0; g < ngroups; g++) {
+        const uint64_t c0 = cols * g / ngroups, c1 = cols * (g + 1) / ngroups;
+        if (c1 == c0) continue;
+        MS_CUDA(c, cudaMemcpyAsync(din.as<T>() + c0 * n, h_in + c0 * n, (c1 - c0) * n * sizeof(T), cudaMemcpyHostToDevice,
+                                   c->copy_stream));
+        cudaEvent_t up = events.make();
+        MS_CUDA(c, cudaEventRecord(up, c->copy_stream));
+        MS_CUDA(c, cudaStreamWaitEvent(c->stream, up, 0));
+        MS_TRY(lde_batch<F>(c, din.as<T>() + c0 * n, n, c1 - c0, ilog2(n), ilog2(blowup), (T)(shift % (uint64_t)F::P), false,
+                            dout.as<T>() + c0 * L, L));
+    }
+    cudaEvent_t drained[2] = {nullptr, nullptr};
+    for (uint64_t i = 0; i < nchunks; i++) {
+        const uint64_t r0 = i * chunk_rows;
+        if (r0 >= L) break;
+        const uint64_t rows = (L - r0 < chunk_rows) ? L - r0 : chunk_rows;
+        T* stage = (i & 1) ? stage1.as<T>() : stage0.as<T>();
+        if (drained[i & 1]) MS_CUDA(c, cudaStreamWaitEvent(c->stream, drained[i & 1], 0));
+        MS_TRY(transpose<F>(c, dout.as<T>() + r0, stage, rows, cols, false, L));
+        cudaEvent_t done = events.make();
+        MS_CUDA(c, cudaEventRecord(done, c->stream));
+        MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, done, 0));
+        MS_CUDA(c, cudaMemcpyAsync(h_out + r0 * cols, stage, rows * cols * sizeof(T), cudaMemcpyDeviceToHost, c->copy_stream));
+        drained[i & 1] = events.make();
+        MS_CUDA(c, cudaEventRecord(drained[i & 1], c->copy_stream));
+    }
+    MS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
     return MS_OK;
 }

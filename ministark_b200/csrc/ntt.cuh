@@ -614,8 +614,8 @@ k_ntt_fixed(const NttTile<F> g) {
 
 template <class F>
 __global__ void k_transpose(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, uint64_t rows,
-                            uint64_t width, int to_colmajor) {
-    // in row-major [rows][width] <-> out column-major [width][rows]; 32x32 tiles through shared memory
+                            uint64_t width, uint64_t cm_stride, int to_colmajor) {
+    // row-major [rows][width] <-> column-major [width][cm_stride >= rows]; 32x32 tiles through shared memory
     __shared__ typename F::T tile[32][33];
     uint64_t r0 = (uint64_t)blockIdx.x * 32, c0 = (uint64_t)blockIdx.y * 32;
     if (to_colmajor) {
@@ -626,12 +626,12 @@ __global__ void k_transpose(const typename F::T* __restrict__ in, typename F::T*
         __syncthreads();
         for (int i = threadIdx.y; i < 32; i += blockDim.y) {
             uint64_t c = c0 + i, r = r0 + threadIdx.x;
-            if (r < rows && c < width) out[c * rows + r] = tile[threadIdx.x][i];
+            if (r < rows && c < width) out[c * cm_stride + r] = tile[threadIdx.x][i];
         }
     } else {
         for (int i = threadIdx.y; i < 32; i += blockDim.y) {
             uint64_t c = c0 + i, r = r0 + threadIdx.x;
-            if (r < rows && c < width) tile[threadIdx.x][i] = in[c * rows + r];
+            if (r < rows && c < width) tile[threadIdx.x][i] = in[c * cm_stride + r];
         }
         __syncthreads();
         for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -920,11 +920,13 @@ int selftest_ops(Ctx* c, uint64_t n_random, uint64_t* n_bad) {
     return MS_OK;
 }
 
+// cm_stride = elements between columns of the column-major side (0: rows)
 template <class F>
-int transpose(Ctx* c, const typename F::T* d_in, typename F::T* d_out, uint64_t rows, uint64_t width, bool to_colmajor) {
+int transpose(Ctx* c, const typename F::T* d_in, typename F::T* d_out, uint64_t rows, uint64_t width, bool to_colmajor,
+              uint64_t cm_stride = 0) {
     if (rows == 0 || width == 0) return MS_OK;
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((width + 31) / 32));
-    k_transpose<F><<<grid, dim3(32, 8), 0, c->stream>>>(d_in, d_out, rows, width, to_colmajor ? 1 : 0);
+    k_transpose<F><<<grid, dim3(32, 8), 0, c->stream>>>(d_in, d_out, rows, width, cm_stride ? cm_stride : rows, to_colmajor ? 1 : 0);
     MS_LAUNCH_CHECK(c);
     return MS_OK;
 }

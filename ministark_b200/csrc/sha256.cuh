@@ -33,6 +33,37 @@ __constant__ uint32_t SHA_ROT_MUL[32] = {
     1u << 21,  1u << 20, 1u << 19, 1u << 18, 1u << 17, 1u << 16, 1u << 15, 1u << 14, 1u << 13, 1u << 12, 1u << 11,
     1u << 10,  1u << 9,  1u << 8,  1u << 7,  1u << 6,  1u << 5,  1u << 4,  1u << 3,  1u << 2,  1u << 1};
 #endif
+// Adds on the FMA pipe.  ncu (profiles/r01_d_ncu_merkle.txt) shows the hashing kernels ALU-pipe bound
+// (88-95 % ALU, 6-10 % FMA): every SHF / LOP3 / IADD3 issues on the ALU pipe.  a + b is also a * 1 + b,
+// an IMAD on the idle FMA pipe at the same issue rate; the multiplier comes from constant memory so
+// that ptxas cannot fold it back into an IADD3.  MS_SHA_IMAD_ADD selects where: 1 the t1 chain,
+// 2 e = d + t1, 4 t2 / a, 8 the message schedule, 16 the final state update.
+#ifndef MS_SHA_IMAD_ADD
+#define MS_SHA_IMAD_ADD 31
+#endif
+#ifdef __CUDACC__
+__constant__ uint32_t SHA_ONE_OPAQUE = 1u;
+#endif
+template <int WHICH>
+__host__ __device__ __forceinline__ uint32_t sha_add(uint32_t a, uint32_t b, uint32_t one) {
+#ifdef __CUDA_ARCH__
+    if (MS_SHA_IMAD_ADD & WHICH) {
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        return d;
+    }
+#endif
+    (void)one;
+    return a + b;
+}
+__host__ __device__ __forceinline__ uint32_t sha_one() {
+#ifdef __CUDA_ARCH__
+    return SHA_ONE_OPAQUE;
+#else
+    return 1u;
+#endif
+}
+
 // xor of rotr(x, n1), rotr(x, n2) and `third` (a rotate or a shift computed by the caller)
 template <int WHICH>
 __host__ __device__ __forceinline__ uint32_t sha_xor3(uint32_t x, int n1, int n2, uint32_t third) {
@@ -63,6 +94,7 @@ __host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_
         0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
         0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    const uint32_t one = sha_one();
 #pragma unroll
     for (int i = 0; i < 64; i++) {
         uint32_t wi;
@@ -72,18 +104,20 @@ __host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_
             uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
             uint32_t s0 = sha_xor3<4>(w15, 7, 18, w15 >> 3);
             uint32_t s1 = sha_xor3<8>(w2, 17, 19, w2 >> 10);
-            wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+            wi = sha_add<8>(sha_add<8>(w[i & 15], s0, one), sha_add<8>(w[(i + 9) & 15], s1, one), one);
             w[i & 15] = wi;
         }
         uint32_t S1 = sha_xor3<1>(e, 6, 11, sha_rotr(e, 25));
         uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + K[i] + wi;
+        uint32_t t1 = sha_add<1>(sha_add<1>(sha_add<1>(wi, K[i], one), h, one), sha_add<1>(S1, ch, one), one);
         uint32_t S0 = sha_xor3<2>(a, 2, 13, sha_rotr(a, 22));
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        uint32_t t2 = sha_add<4>(S0, mj, one);
+        h = g; g = f; f = e; e = sha_add<2>(d, t1, one); d = c; c = b; b = a; a = sha_add<4>(t1, t2, one);
     }
-    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    st[0] = sha_add<16>(st[0], a, one); st[1] = sha_add<16>(st[1], b, one); st[2] = sha_add<16>(st[2], c, one);
+    st[3] = sha_add<16>(st[3], d, one); st[4] = sha_add<16>(st[4], e, one); st[5] = sha_add<16>(st[5], f, one);
+    st[6] = sha_add<16>(st[6], g, one); st[7] = sha_add<16>(st[7], h, one);
 }
 
 // The last block of a message whose length is a multiple of 64 bytes is a constant: 0x80, zeros, the
@@ -120,17 +154,20 @@ template <uint32_t BITS>
 __host__ __device__ __forceinline__ void sha256_compress_padblock(uint32_t st[8]) {
     constexpr ShaPadKW KW = sha_pad_kw(BITS);
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    const uint32_t one = sha_one();
 #pragma unroll
     for (int i = 0; i < 64; i++) {
         uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
         uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + KW.v[i];
+        uint32_t t1 = sha_add<1>(sha_add<1>(h, KW.v[i], one), sha_add<1>(S1, ch, one), one);
         uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        uint32_t t2 = sha_add<4>(S0, mj, one);
+        h = g; g = f; f = e; e = sha_add<2>(d, t1, one); d = c; c = b; b = a; a = sha_add<4>(t1, t2, one);
     }
-    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    st[0] = sha_add<16>(st[0], a, one); st[1] = sha_add<16>(st[1], b, one); st[2] = sha_add<16>(st[2], c, one);
+    st[3] = sha_add<16>(st[3], d, one); st[4] = sha_add<16>(st[4], e, one); st[5] = sha_add<16>(st[5], f, one);
+    st[6] = sha_add<16>(st[6], g, one); st[7] = sha_add<16>(st[7], h, one);
 }
 
 }  // namespace ms

@@ -72,6 +72,19 @@ def test_coset_lde_max_two_pass_size(ctxs, oracle):
     assert (got[0] == want[:, 0]).all()
 
 
+@pytest.mark.parametrize("field,log_n,cols", [(GL, 20, 9), (BB, 21, 12)])
+def test_coset_lde_host_pipelined_equals_device(field, log_n, cols, ctxs):
+    """The host-buffer call pipelines column groups (upload against kernels) and row chunks (transpose
+    against download) once the buffers are large; the result must equal the device-resident call."""
+    ctx = ctxs[field]
+    n = 1 << log_n
+    coeffs = rand_field(field, (cols, n), 31)
+    got_h = ctx.coset_lde_host(coeffs, 4, 11)  # row-major [L, cols]
+    got_d = ctx.to_host(ctx.coset_lde(ctx.to_device(coeffs), 4, 11))  # [cols, L]
+    assert got_h.shape == (4 * n, cols)
+    assert (got_h.T == got_d).all()
+
+
 def test_lde_rejects_bad_shapes(ctxs):
     from ministark_b200 import MiniStarkError
 
