@@ -31,8 +31,9 @@ sys.path.insert(0, ROOT)
 GL = 0
 P_GL = 2**64 - 2**32 + 1
 SHIFT = 0x123456789ABCDEF % P_GL  # fixed coset offset for the stage benchmark (injected challenge)
-# measured once under ncu for the headline shape (see profiles/): 5.45 GB (pass 1) + 8.54 GB (pass 2)
-NCU_TRAFFIC_BYTES = 13_990_000_000
+# measured under ncu --set full for the headline shape (profiles/r01_d_ncu_ntt.txt):
+# pass 1 1.211 + 4.320 GB, pass 2 4.295 + 4.404 GB (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_TRAFFIC_BYTES = 14_230_000_000
 
 
 def parse():
@@ -322,7 +323,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES if (args.log_rows, C, B) == (22, 32, 4) else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, pass 1 + pass 2 "
-                                           "(profiles/r01_c_ncu_ntt_fixed.txt)",
+                                           "(profiles/r01_d_ncu_ntt.txt)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel": "coset-LDE = k_ntt_fixed pass 1 + pass 2 (+ twiddle builders), one ms_coset_lde call; "

@@ -204,6 +204,25 @@ int32_t ms_merkle_reduce(ms_ctx* ctx, const uint32_t* d_digests, uint64_t n, uin
 int32_t ms_merkle_subtree(ms_ctx* ctx, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width, int32_t deg,
                           uint64_t leafs_per_node, uint64_t inner_children, uint32_t* d_digests_out, uint64_t* n_out);
 
+/* ms_merkle_subtree over a row range whose coordinate planes are given one pointer each
+ * (plane_ptrs_host: HOST array of width*deg DEVICE pointers, plane p = column p/deg, coordinate p%deg,
+ * each pointing at the first row of the range).  The planes may be peer-GPU memory opened with
+ * ms_peer_open: the leaf kernel then reads the other ranks' LDE columns over NVLink while it hashes,
+ * which replaces the column-to-row exchange in front of the row-sharded LDE tree (src/starks.rs:92-94
+ * on a column-sharded matrix).  Same digests as ms_merkle_subtree on the gathered block. */
+int32_t ms_merkle_subtree_gather(ms_ctx* ctx, const void* const* plane_ptrs_host, uint64_t rows, uint64_t width, int32_t deg,
+                                 uint64_t leafs_per_node, uint64_t inner_children, uint32_t* d_digests_out, uint64_t* n_out);
+
+/* Peer memory for the gather above (CUDA IPC, one process per GPU on one node): a buffer from
+ * ms_peer_alloc can be exported as a 64-byte handle, sent to the other ranks by any means, and opened
+ * there; the returned pointer is valid in kernels of the opening context's device.  No reference call
+ * site: the reference is single-process. */
+int32_t ms_peer_alloc(ms_ctx* ctx, uint64_t bytes, void** d_out);
+int32_t ms_peer_free(ms_ctx* ctx, void* d_ptr);
+int32_t ms_peer_export(ms_ctx* ctx, void* d_ptr, uint8_t* handle64);
+int32_t ms_peer_open(ms_ctx* ctx, const uint8_t* handle64, void** d_out);
+int32_t ms_peer_close(ms_ctx* ctx, void* d_ptr);
+
 /* per-stage device times (ms) of the last ms_stark_prove* call: fills up to `cap` entries, returns count.
  * names[i] points to static strings. */
 int32_t ms_stark_last_timings(ms_ctx* ctx, const char** names, float* ms, int32_t cap);

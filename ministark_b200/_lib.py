@@ -72,6 +72,12 @@ SIGNATURES = {
     "ms_stark_prove_hooked": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
     "ms_merkle_subtree": (_i32, [_vp, _vp, _u64, _u64, _u64, _i32, _u64, _u64, _vp, C.POINTER(_u64)]),
     "ms_merkle_reduce": (_i32, [_vp, _vp, _u64, _u64, _vp]),
+    "ms_merkle_subtree_gather": (_i32, [_vp, _vp, _u64, _u64, _i32, _u64, _u64, _vp, C.POINTER(_u64)]),
+    "ms_peer_alloc": (_i32, [_vp, _u64, C.POINTER(_vp)]),
+    "ms_peer_free": (_i32, [_vp, _vp]),
+    "ms_peer_export": (_i32, [_vp, _vp, _vp]),
+    "ms_peer_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    "ms_peer_close": (_i32, [_vp, _vp]),
     "ms_stark_last_timings": (_i32, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i32]),
 }
 

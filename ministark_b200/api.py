@@ -47,6 +47,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            ops = getattr(self, "_sharded_ops", None)
+            if ops is not None:
+                ops.close_peers()  # unmap / free the CUDA-IPC exchange buffers (all device work is done by now)
             self.lib.ms_ctx_destroy(self.h)
             self.h = None
 

@@ -322,6 +322,46 @@ int32_t ms_merkle_subtree(ms_ctx* c, const void* d_data, uint64_t stride, uint64
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }
+int32_t ms_merkle_subtree_gather(ms_ctx* c, const void* const* plane_ptrs_host, uint64_t rows, uint64_t width, int32_t deg,
+                                 uint64_t lpn, uint64_t k, uint32_t* d_out, uint64_t* n_out) {
+    if (!plane_ptrs_host || deg < 1 || width == 0) return fail(c, MS_ERR_BAD_SHAPE, "ms_merkle_subtree_gather: null plane table");
+    Scratch tab(c);
+    const size_t bytes = (size_t)width * (size_t)deg * sizeof(void*);
+    MS_TRY(tab.alloc(bytes));
+    MS_CUDA(c, cudaMemcpyAsync(tab.p, plane_ptrs_host, bytes, cudaMemcpyHostToDevice, c->stream));
+#define CALL(F) merkle_subtree<F>(c, (const F::T*)tab.p, 0, rows, width, deg, lpn, k, d_out, n_out, true)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+/* ---- peer memory (CUDA IPC): buffers other ranks' kernels read over NVLink ------------------- */
+int32_t ms_peer_alloc(ms_ctx* c, uint64_t bytes, void** d_out) {
+    if (!d_out) return fail(c, MS_ERR_BAD_SHAPE, "ms_peer_alloc: null out");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaMalloc(d_out, bytes ? bytes : 16));
+    return MS_OK;
+}
+int32_t ms_peer_free(ms_ctx* c, void* d_ptr) {
+    if (d_ptr) MS_CUDA(c, cudaFree(d_ptr));
+    return MS_OK;
+}
+int32_t ms_peer_export(ms_ctx* c, void* d_ptr, uint8_t* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    MS_CUDA(c, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64, &h, 64);
+    return MS_OK;
+}
+int32_t ms_peer_open(ms_ctx* c, const uint8_t* handle64, void** d_out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return MS_OK;
+}
+int32_t ms_peer_close(ms_ctx* c, void* d_ptr) {
+    if (d_ptr) MS_CUDA(c, cudaIpcCloseMemHandle(d_ptr));
+    return MS_OK;
+}
 int32_t ms_merkle_reduce(ms_ctx* c, const uint32_t* d_digests, uint64_t n, uint64_t k, uint8_t* root32) {
     return merkle_reduce(c, d_digests, n, k, root32);
 }

@@ -33,13 +33,17 @@ __constant__ uint32_t SHA_ROT_MUL[32] = {
     1u << 21,  1u << 20, 1u << 19, 1u << 18, 1u << 17, 1u << 16, 1u << 15, 1u << 14, 1u << 13, 1u << 12, 1u << 11,
     1u << 10,  1u << 9,  1u << 8,  1u << 7,  1u << 6,  1u << 5,  1u << 4,  1u << 3,  1u << 2,  1u << 1};
 #endif
-// Adds on the FMA pipe.  ncu (profiles/r01_d_ncu_merkle.txt) shows the hashing kernels ALU-pipe bound
-// (88-95 % ALU, 6-10 % FMA): every SHF / LOP3 / IADD3 issues on the ALU pipe.  a + b is also a * 1 + b,
-// an IMAD on the idle FMA pipe at the same issue rate; the multiplier comes from constant memory so
-// that ptxas cannot fold it back into an IADD3.  MS_SHA_IMAD_ADD selects where: 1 the t1 chain,
-// 2 e = d + t1, 4 t2 / a, 8 the message schedule, 16 the final state update.
+// Adds on the FMA pipe (experiment, OFF).  ncu (profiles/r01_d_ncu_merkle.txt) shows the hashing kernels
+// ALU-pipe bound (88-95 % ALU, 6-10 % FMA): every SHF / LOP3 / IADD3 issues on the ALU pipe.  a + b is
+// also a * 1 + b, an IMAD on the idle FMA pipe; the multiplier comes from constant memory so that ptxas
+// cannot fold it back into an IADD3.  MS_SHA_IMAD_ADD selects where: 1 the t1 chain, 2 e = d + t1,
+// 4 t2 / a, 8 the message schedule, 16 the final state update.  Measured on B200 with every add moved
+// (ALU instructions per binary node 2108 -> 1656, FMA 178 -> 992): LDE tree 16.68 -> 16.79 ms, i.e. no
+// gain.  profiles/r01_d_pipes.txt explains it: two pipes only overlap while the register-file operand
+// bandwidth lasts (~1.7 register reads per clock per scheduler), ptxas keeps the multiplier in a vector
+// register (IMAD R, R, R, R: three reads), and the extra reads cost what the freed ALU slots gain.
 #ifndef MS_SHA_IMAD_ADD
-#define MS_SHA_IMAD_ADD 31
+#define MS_SHA_IMAD_ADD 0
 #endif
 #ifdef __CUDACC__
 __constant__ uint32_t SHA_ONE_OPAQUE = 1u;
@@ -83,7 +87,7 @@ __host__ __device__ __forceinline__ void sha256_init(uint32_t st[8]) {
 
 // One compression: st <- st + F(st, w).  w[16] is the big-endian-decoded block and is clobbered
 // (rolling message schedule kept in the same 16 registers).
-__host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+__host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], uint32_t one = sha_one()) {
     constexpr uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
         0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
@@ -94,7 +98,6 @@ __host__ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_
         0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
         0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-    const uint32_t one = sha_one();
 #pragma unroll
     for (int i = 0; i < 64; i++) {
         uint32_t wi;
@@ -151,10 +154,9 @@ constexpr ShaPadKW sha_pad_kw(uint32_t bits) {
     return r;
 }
 template <uint32_t BITS>
-__host__ __device__ __forceinline__ void sha256_compress_padblock(uint32_t st[8]) {
+__host__ __device__ __forceinline__ void sha256_compress_padblock(uint32_t st[8], uint32_t one = sha_one()) {
     constexpr ShaPadKW KW = sha_pad_kw(BITS);
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-    const uint32_t one = sha_one();
 #pragma unroll
     for (int i = 0; i < 64; i++) {
         uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);

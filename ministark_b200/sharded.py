@@ -15,6 +15,16 @@ only") runs identically on every rank, so all ranks derive the same challenges w
 and rank 0's proof is the proof.  The exchange is the only bulk collective: L*C*s*(G-1)/G^2 bytes out
 per GPU.
 
+Two ways to do the exchange (MINISTARK_EXCHANGE = "peer" | "nccl", default "peer" on GPUs):
+  peer   no exchange pass at all: every rank's LDE columns live in a CUDA-IPC buffer the other ranks
+         have opened, and the leaf-hash kernel of rank h loads rows [h L/G, (h+1) L/G) of every column
+         straight from its owner over NVLink while it hashes (ms_merkle_subtree_gather): the transfer
+         is hidden under the SHA-256 arithmetic, and the [C][L/G] receive block is never materialised.
+         Two tiny all-reduces order the ranks (all LDEs done before anyone reads; all reads done before
+         anyone overwrites its columns -- the second one is the digest all-gather that is needed anyway).
+  nccl   grouped ncclSend/ncclRecv into a [C][L/G] block, then a local ms_merkle_subtree (the baseline,
+         and what the CPU gloo tests exercise).
+
 The compute calls go through a small `ops` object: CudaOps (the C ABI, the product path) or, in the
 CPU-only gloo tests, an oracle-backed stand-in defined under tests/.
 """
@@ -125,6 +135,65 @@ class CudaOps:
         self.ctx._check(self.lib.ms_merkle_reduce(self.ctx.h, C.c_void_p(digests.data_ptr()), n, k, root))
         return bytes(root)
 
+    # ---- peer memory (CUDA IPC) for the exchange-free LDE tree
+    def lde_raw(self, coeffs_ptr: int, n: int, ncols: int, blowup: int, shift: int, out_ptr: int, out_stride: int):
+        self.ctx._check(self.lib.ms_coset_lde(self.ctx.h, C.c_void_p(coeffs_ptr), n, n, ncols, blowup, shift,
+                                              C.c_void_p(out_ptr), out_stride))
+
+    def subtree_gather(self, plane_ptrs: Sequence[int], rows: int, width: int, lpn: int, k: int, out_digests) -> int:
+        tab = (C.c_void_p * len(plane_ptrs))(*plane_ptrs)
+        n_out = C.c_uint64(0)
+        self.ctx._check(self.lib.ms_merkle_subtree_gather(self.ctx.h, tab, rows, width, 1, lpn, k,
+                                                          C.c_void_p(out_digests.data_ptr()), C.byref(n_out)))
+        return int(n_out.value)
+
+    def peer_buffers(self, key, nbytes: int, dist, group):
+        """This rank's IPC-exported buffer of `nbytes` plus every rank's view of every other rank's buffer:
+        returns [ptr_of_rank_0, ..., ptr_of_rank_{G-1}] (own entry = the local pointer).  Cached per key."""
+        import torch
+
+        cache = self.__dict__.setdefault("_peer", {})
+        if key in cache:
+            return cache[key][0]
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = C.c_void_p()
+        self.ctx._check(self.lib.ms_peer_alloc(self.ctx.h, nbytes, C.byref(mine)))
+        handle = (C.c_uint8 * 64)()
+        self.ctx._check(self.lib.ms_peer_export(self.ctx.h, mine, handle))
+        dev = f"cuda:{self.ctx.device}"
+        local = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, local, group=group)
+        allh = allh.cpu().numpy()
+        ptrs = []
+        for g in range(world):
+            if g == rank:
+                ptrs.append(int(mine.value))
+                continue
+            h = (C.c_uint8 * 64)(*allh[g * 64:(g + 1) * 64].tolist())
+            p = C.c_void_p()
+            self.ctx._check(self.lib.ms_peer_open(self.ctx.h, h, C.byref(p)))
+            ptrs.append(int(p.value))
+        cache[key] = (ptrs, rank)
+        return ptrs
+
+    def close_peers(self, dist=None, group=None):
+        """Unmap the peers' buffers and free the own ones (every rank must call it: a barrier first makes sure
+        nobody still reads)."""
+        cache = self.__dict__.pop("_peer", {})
+        if not cache:
+            return
+        if dist is not None:
+            dist.barrier(group=group)
+        for ptrs, rank in cache.values():
+            for g, p in enumerate(ptrs):
+                if g != rank:
+                    self.lib.ms_peer_close(self.ctx.h, C.c_void_p(p))
+        if dist is not None:
+            dist.barrier(group=group)
+        for ptrs, rank in cache.values():
+            self.lib.ms_peer_free(self.ctx.h, C.c_void_p(ptrs[rank]))
+
 
 
 # ------------------------------------------------------------------------------------------ the committer
@@ -142,6 +211,10 @@ class ShardedCommitter:
         self.world = dist.get_world_size(group) if dist is not None else 1
         self.stats = {"exchange_bytes_out": 0, "lde_cols": 0}
         self._keep = None
+        import os
+
+        want = os.environ.get("MINISTARK_EXCHANGE", "peer")
+        self.exchange = "peer" if (want == "peer" and self.world > 1 and hasattr(ops, "peer_buffers")) else "nccl"
 
     # ---- shared: gather every rank's digests and join them
     def _join(self, mine, n_mine: int) -> bytes:
@@ -186,6 +259,8 @@ class ShardedCommitter:
         plan = SubtreePlan.make(L, self.k, self.world)
         rows = plan.groups_per_rank
         a, b = column_ranges(cols, self.world)[self.rank]
+        if self.exchange == "peer":
+            return self._lde_commit_peer(coeffs_ptr, n, cols, blowup, shift, plan)
         t0 = self._mark()
         mine = self.ops.empty(max(b - a, 1), L)
         if b > a:
@@ -205,6 +280,7 @@ class ShardedCommitter:
             for wk in work:
                 wk.wait()
             self.stats["exchange_bytes_out"] = len(sends) * rows * self.ops.elem
+        self.stats["exchange"] = "nccl-sendrecv"
         t2 = self._mark()
         digests = self.ops.empty_digests(max(plan.digests_per_rank, 1))
         got = self.ops.subtree(block.data_ptr(), block.stride(0), rows, cols, self.lpn, self.k, digests)
@@ -215,6 +291,37 @@ class ShardedCommitter:
             t3.synchronize()
             self.stats.update(lde_ms=t0.elapsed_time(t1), exchange_ms=t1.elapsed_time(t2), tree_ms=t2.elapsed_time(t3))
         self._keep = (mine, block)  # alive until the stream has consumed them
+        return root
+
+    def _lde_commit_peer(self, coeffs_ptr: int, n: int, cols: int, blowup: int, shift: int, plan: SubtreePlan) -> bytes:
+        """a4 + a5 without an exchange pass: the leaf kernel reads the peers' columns over NVLink."""
+        import torch
+
+        ops, d = self.ops, self.dist
+        L, rows, elem = n * blowup, plan.groups_per_rank, self.ops.elem
+        ranges = column_ranges(cols, self.world)
+        a, b = ranges[self.rank]
+        most = max(hi - lo for lo, hi in ranges)
+        bases = ops.peer_buffers(("lde", most, L), most * L * elem, d, self.group)
+        flag = ops.__dict__.setdefault("_flag", torch.zeros(1, dtype=torch.int32, device=f"cuda:{ops.ctx.device}"))
+        t0 = self._mark()
+        if b > a:
+            ops.lde_raw(coeffs_ptr + a * n * elem, n, b - a, blowup, shift, bases[self.rank], L)
+        self.stats["lde_cols"] = b - a
+        t1 = self._mark()
+        d.all_reduce(flag, group=self.group)  # every rank's columns are complete (stream-ordered)
+        t2 = self._mark()
+        planes = [bases[g] + ((c - lo) * L + self.rank * rows) * elem for g, (lo, hi) in enumerate(ranges) for c in range(lo, hi)]
+        digests = ops.empty_digests(max(plan.digests_per_rank, 1))
+        got = ops.subtree_gather(planes, rows, cols, self.lpn, self.k, digests)
+        assert got == plan.digests_per_rank
+        t3 = self._mark()
+        root = self._join(digests, got)  # the all-gather also tells every rank that its columns were read
+        self.stats["exchange_bytes_out"] = (cols - (b - a)) * rows * elem  # pulled over NVLink by the leaf kernel
+        self.stats["exchange"] = "peer-read"
+        if t0 is not None:
+            t3.synchronize()
+            self.stats.update(lde_ms=t0.elapsed_time(t1), exchange_ms=t1.elapsed_time(t2), tree_ms=t2.elapsed_time(t3))
         return root
 
     def _peer(self, group_rank: int) -> int:

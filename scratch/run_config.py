@@ -26,7 +26,7 @@ trace_rm = synth_trace(0, n, W, seed=0x5EED000000000001)
 m = synth_linear_matrix(0, n, W)
 params = StarkParams(sec, B, n - 1, C, k)
 bound = int(ctx.lib.ms_stark_proof_bound(0, params, n, C))
-buf = torch.empty(bound if rank == 0 else 64, dtype=torch.uint8).pin_memory().numpy()
+buf = torch.empty(bound, dtype=torch.uint8).pin_memory().numpy() if rank == 0 else np.empty(bound, dtype=np.uint8)  # replicas only write the fixed part
 trace_cm = ctx.to_device(np.ascontiguousarray(trace_rm.T))
 del trace_rm
 times, ln, stages = [], 0, None

@@ -24,6 +24,13 @@ __global__ void __launch_bounds__(512) k(uint32_t* out, uint32_t seed, long long
             if (op == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
             if (op == 5) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
             if (op == 6) asm volatile("{add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;}" : "+r"(x[i]), "+r"(y[i]) : "r"(z[i]), "r"(seed));
+            if (op == 8) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(x[i]));
+            if (op == 9) asm volatile("add.u32 %0, %0, 0x12345;" : "+r"(x[i]));
+            if (op == 10) asm volatile("lop3.b32 %0, %0, %1, 0x0f0f1234, 0x96;" : "+r"(x[i]) : "r"(y[i]));
+            if (op == 11) asm volatile("mad.lo.u32 %0, %0, %1, 0x12345;" : "+r"(x[i]) : "r"(y[i]));
+            if (op == 12) asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+            if (op == 13) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+            if (op == 14) asm volatile("mad.lo.u32 %0, %0, 0x10001, %1;" : "+r"(x[i]) : "r"(y[i]));
             if (op == 7) asm volatile("{mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;}" : "+r"(x[i]), "+r"(y[i]) : "r"(z[i]), "r"(seed));
         }
     }
@@ -39,20 +46,25 @@ void run(const char* name) {
     const int blocks = 148 * 2, threads = 512;
     uint32_t* out; long long* cyc;
     cudaMalloc(&out, blocks * threads * 4); cudaMalloc(&cyc, blocks * 8);
-    k<A, NA, B, NB><<<blocks, threads>>>(out, 12345, cyc);
-    cudaDeviceSynchronize();
+    double avg = 1e30; float ms = 1e30f;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0);
-    k<A, NA, B, NB><<<blocks, threads>>>(out, 12345, cyc);
-    cudaEventRecord(e1); cudaEventSynchronize(e1);
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    long long h[296]; cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
-    double avg = 0; for (int i = 0; i < blocks; i++) avg += h[i]; avg /= blocks;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        k<A, NA, B, NB><<<blocks, threads>>>(out, 12345, cyc);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float m = 0; cudaEventElapsedTime(&m, e0, e1);
+        long long h[296]; cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+        double a = 0; for (int i = 0; i < blocks; i++) a += h[i]; a /= blocks;
+        if (a < avg) avg = a;
+        if (m < ms) ms = m;
+    }
     double ops = 32.0 * ITERS * (NA + NB);  // PTX-level ops per SM (32 warps)
     printf("%-26s %8.0f cyc %.3f ms => clock64 %.0f MHz | %.2f ops/clk/SM (%.2f clk/op/SMSP)\n", name, avg, ms, avg / ms / 1e3, ops / avg, avg / (8.0 * ITERS * (NA + NB)));
     cudaFree(out); cudaFree(cyc);
 }
+__global__ void spin(long long n) { long long t = clock64(); while (clock64() - t < n) {} }
 int main() {
+    spin<<<148, 128>>>(1500000000LL); cudaDeviceSynchronize();  // ~1 s: let the clocks ramp
     run<0, 16, 0, 0>("IMAD x16");
     run<1, 16, 0, 0>("IMAD.HI x16");
     run<2, 16, 0, 0>("IMAD.WIDE x16");
@@ -69,5 +81,19 @@ int main() {
     run<2, 5, 4, 10>("IMAD.WIDE x5 + LOP3 x10");
     run<1, 4, 3, 12>("IMAD.HI x4 + IADD3 x12");
     run<5, 8, 4, 8>("SHF x8 + LOP3 x8");
+    run<8, 16, 0, 0>("ROT imm (SHF x,x,imm) x16");
+    run<9, 16, 0, 0>("ADD imm (1 reg) x16");
+    run<10, 16, 0, 0>("LOP3 2 reg + imm x16");
+    run<11, 16, 0, 0>("IMAD a*b+imm x16");
+    run<14, 16, 0, 0>("IMAD a*imm+c x16");
+    run<12, 16, 0, 0>("XOR 2-input x16");
+    run<13, 16, 0, 0>("ADD 2-input x16");
+    run<8, 8, 14, 8>("ROT x8 + IMAD(a*imm+c) x8");
+    run<8, 8, 0, 8>("ROT x8 + IMAD 3reg x8");
+    run<8, 8, 13, 8>("ROT x8 + ADD2 x8");
+    run<4, 8, 0, 8>("LOP3 x8 + IMAD x8");
+    run<4, 8, 14, 8>("LOP3 x8 + IMAD(a*imm+c) x8");
+    run<12, 8, 14, 8>("XOR2 x8 + IMAD(a*imm+c) x8");
+    run<13, 8, 14, 8>("ADD2 x8 + IMAD(a*imm+c) x8");
     return 0;
 }

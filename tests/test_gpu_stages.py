@@ -126,6 +126,39 @@ def test_merkle_commit_base(field, rows, width, lpn, k, ctxs, oracle):
 
 
 @pytest.mark.parametrize("field", [GL, BB])
+@pytest.mark.parametrize("rows,width,k,parts", [(64, 4, 2, 2), (256, 16, 4, 4), (512, 7, 8, 3), (4096, 32, 2, 8)])
+def test_merkle_subtree_gather_equals_block(field, rows, width, k, parts, ctxs, oracle):
+    """ms_merkle_subtree_gather (one pointer per column: columns scattered over separate allocations, as the
+    column-sharded LDE is over the ranks' peer buffers) leaves the digests of ms_merkle_subtree on the
+    contiguous block, for every row range of the split."""
+    import ctypes as C
+    import torch
+
+    ctx = ctxs[field]
+    flat = edge_values(field, rows * width, rows * 3 + width)
+    cm = ctx.to_device(np.ascontiguousarray(flat.reshape(rows, width).T))  # [width, rows]
+    # scatter the columns over `parts` separately allocated tensors with their own strides
+    owners = [ctx.empty(width, rows + 16 * (g + 1)) for g in range(parts)]
+    for c in range(width):
+        owners[c % parts][c, :rows] = cm[c]
+    elem = 8 if field == GL else 4
+    ranges = 4 if rows >= 256 else 2
+    per = rows // ranges
+    for h in range(ranges):
+        want = torch.empty(k, 8, dtype=torch.int32, device=cm.device)
+        n_want = C.c_uint64(0)
+        ctx._check(ctx.lib.ms_merkle_subtree(ctx.h, C.c_void_p(cm.data_ptr() + h * per * elem), rows, per, width, 1, width, k,
+                                             C.c_void_p(want.data_ptr()), C.byref(n_want)))
+        ptrs = [owners[c % parts][c].data_ptr() + h * per * elem for c in range(width)]
+        tab = (C.c_void_p * width)(*ptrs)
+        got = torch.empty(k, 8, dtype=torch.int32, device=cm.device)
+        n_got = C.c_uint64(0)
+        ctx._check(ctx.lib.ms_merkle_subtree_gather(ctx.h, tab, per, width, 1, width, k, C.c_void_p(got.data_ptr()), C.byref(n_got)))
+        assert n_got.value == n_want.value >= 1
+        assert (got[: n_got.value] == want[: n_want.value]).all()
+
+
+@pytest.mark.parametrize("field", [GL, BB])
 @pytest.mark.parametrize("n", [2, 4, 64, 4096])
 def test_merkle_commit_ext_leaves(field, n, ctxs, oracle):
     """FRI trees: leaf groups of 2 extension elements, Display 'QuadExtField(..)' (fri.rs:351)."""

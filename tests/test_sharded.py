@@ -216,9 +216,14 @@ def _nccl_worker(rank, world, port, log_n, w, blowup, k, q):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("k", [2, 4])
-def test_sharded_prover_multi_gpu_equals_single(k):
+def test_sharded_prover_multi_gpu_equals_single(k, exchange, monkeypatch):
+    """peer: the leaf kernel reads the other ranks' LDE columns over NVLink (CUDA IPC, no exchange pass);
+    nccl: grouped send/recv into a row block.  Both must give the single-GPU proof byte for byte."""
     import torch
+
+    monkeypatch.setenv("MINISTARK_EXCHANGE", exchange)  # inherited by the spawned ranks
     import torch.multiprocessing as mp
 
     world = min(torch.cuda.device_count(), 4)
