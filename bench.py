@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 GL = 0
 P_GL = 2**64 - 2**32 + 1
 SHIFT = 0x123456789ABCDEF % P_GL  # fixed coset offset for the stage benchmark (injected challenge)
-# measured under ncu --set full for the headline shape (profiles/r01_d_ncu_ntt.txt):
-# pass 1 1.211 + 4.320 GB, pass 2 4.295 + 4.404 GB (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_TRAFFIC_BYTES = 14_230_000_000
+# measured under ncu --set full for the headline shape (profiles/r01_e_ncu_ntt.txt):
+# pass 1 1.211 + 4.257 GB, pass 2 4.297 + 4.268 GB (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_TRAFFIC_BYTES = 14_033_000_000
 
 
 def parse():
@@ -323,7 +323,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES if (args.log_rows, C, B) == (22, 32, 4) else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, pass 1 + pass 2 "
-                                           "(profiles/r01_d_ncu_ntt.txt)",
+                                           "(profiles/r01_e_ncu_ntt.txt)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel": "coset-LDE = k_ntt_fixed pass 1 + pass 2 (+ twiddle builders), one ms_coset_lde call; "

@@ -22,6 +22,7 @@ struct Ctx {
     std::string err;
     int zero_display_empty = 0;  // ark-ff 0.4 printed "" for zero; 0.5.0 prints "0" 
     void* wtab[2] = {nullptr, nullptr};  // plain DIT twiddles, forward / inverse (see ntt.cuh)
+    void* tw16_plain[2][16] = {};        // plain block-twiddle tables per direction and transform size (ntt.cuh)
     uint32_t* dec4 = nullptr;            // ASCII of 4-digit groups (see merkle.cuh)
     unsigned long long launches = 0;     // kernels launched by this library (bench gpu_launches)
     // optional per-kernel device timing (bench.py roofline): event pairs collected by ms_profile_collect

@@ -116,6 +116,9 @@ void ms_ctx_destroy(ms_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; i++)
         if (c->wtab[i]) cudaFree(c->wtab[i]);
+    for (int i = 0; i < 2; i++)
+        for (int a = 0; a < 16; a++)
+            if (c->tw16_plain[i][a]) cudaFree(c->tw16_plain[i][a]);
     if (c->dec4) cudaFree(c->dec4);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->copy_event) cudaEventDestroy(c->copy_event);

@@ -157,6 +157,65 @@ struct Fast<GL> {
         return a < t ? d - GL::EPS : d;
 #endif
     }
+    // x * 2^S, 0 < S < 96, x any representative, result canonical.  Every root of unity of order <= 64 is a
+    // power of two in this field (2^96 = -1), so the butterflies inside a radix-16 block multiply by shifts:
+    // with x << r = W2 2^64 + W1 2^32 + W0 the product is  W0 + W1 2^32 + W2 (2^32-1)           (S = r),
+    // W1 2^32 + W2 (2^32-1) - W3 (S = 32 + r)  or  W2 (2^32-1) - W3 - W4 2^32 (S = 64 + r; always canonical),
+    // 9 to 16 instructions against 22 for a general product (and a third of its register reads).
+    template <int S>
+    static MS_HD T mulpow2(T x) {
+        static_assert(S > 0 && S < 96, "shift out of range");
+#ifdef __CUDA_ARCH__
+        constexpr int Q = S / 32, R = S % 32;
+        const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), eps = GL_EPS_OPAQUE;
+        uint32_t a, b, c;  // x << R as three words (R = 0: a = x0, b = x1, c = 0)
+        if constexpr (R == 0) { a = x0; b = x1; c = 0; }
+        else { a = x0 << R; b = __funnelshift_l(x0, x1, R); c = x1 >> ((32 - R) & 31); }
+        uint32_t r0, r1;
+        if constexpr (Q == 0) {
+            asm("{\n\t.reg .u32 k, d, s0, s1;\n\t"
+                "mad.lo.cc.u32 s0, %4, %5, %2;\n\t"
+                "madc.hi.cc.u32 s1, %4, %5, %3;\n\t"
+                "addc.u32 k, 0, 0;\n\t"
+                "add.cc.u32 d, s0, 0xFFFFFFFF;\n\t"
+                "addc.cc.u32 d, s1, 0;\n\t"
+                "addc.u32 k, k, 0;\n\t"
+                "mad.lo.cc.u32 %0, k, %5, s0;\n\t"
+                "madc.hi.u32 %1, k, %5, s1;\n\t}"
+                : "=r"(r0), "=r"(r1) : "r"(a), "r"(b), "r"(c), "r"(eps));
+        } else if constexpr (Q == 1) {
+            asm("{\n\t.reg .u32 k, m, d, s0, s1;\n\t"
+                "sub.cc.u32 s0, 0, %4;\n\t"
+                "subc.cc.u32 s1, %2, 0;\n\t"
+                "subc.u32 m, 0, 0;\n\t"
+                "sub.cc.u32 s0, s0, m;\n\t"
+                "subc.u32 s1, s1, 0;\n\t"
+                "mad.lo.cc.u32 s0, %3, %5, s0;\n\t"
+                "madc.hi.cc.u32 s1, %3, %5, s1;\n\t"
+                "addc.u32 k, 0, 0;\n\t"
+                "add.cc.u32 d, s0, 0xFFFFFFFF;\n\t"
+                "addc.cc.u32 d, s1, 0;\n\t"
+                "addc.u32 k, k, 0;\n\t"
+                "mad.lo.cc.u32 %0, k, %5, s0;\n\t"
+                "madc.hi.u32 %1, k, %5, s1;\n\t}"
+                : "=r"(r0), "=r"(r1) : "r"(a), "r"(b), "r"(c), "r"(eps));
+        } else {
+            asm("{\n\t.reg .u32 m, s0, s1;\n\t.reg .u64 pp;\n\t"
+                "mul.wide.u32 pp, %2, %5;\n\t"
+                "mov.b64 {s0, s1}, pp;\n\t"
+                "sub.cc.u32 s0, s0, %3;\n\t"
+                "subc.cc.u32 s1, s1, %4;\n\t"
+                "subc.u32 m, 0, 0;\n\t"
+                "sub.cc.u32 %0, s0, m;\n\t"
+                "subc.u32 %1, s1, 0;\n\t}"
+                : "=r"(r0), "=r"(r1) : "r"(a), "r"(b), "r"(c), "r"(eps));
+        }
+        return ((uint64_t)r1 << 32) | r0;
+#else
+        constexpr uint64_t pw = S < 64 ? (1ULL << (S & 63)) : (0xFFFFFFFFULL << ((S - 64) & 31));  // 2^S mod p
+        return GL::mul(x % GL::P, pw);
+#endif
+    }
     static MS_HD T canon(T a) {
 #ifdef __CUDA_ARCH__
         // a >= p  <=>  a + (2^32 - 1) carries out of 64 bits; then a - p = a + (2^32 - 1) mod 2^64
@@ -207,6 +266,59 @@ struct Fast<BB> {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Radix-2^G block with power-of-two twiddles (Goldilocks).  The in-register part of a round is a plain
+// DIT DFT of size 2^G <= 16 once every element r has been multiplied by beta^brev(r) (beta = the round's
+// coset / position factor, see fixed_round): its own twiddles are the 2^(st+1)-th roots of unity, all
+// powers of two: w_2 = 2^96, w_4 = 2^48, w_8 = 2^120, w_16 = 2^156 for ark's generator
+// (inverse: 2^96, 2^144, 2^72, 2^36).  Exponents >= 96 use 2^96 = -1: the two butterfly outputs swap.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+struct ShiftTw {
+    static constexpr bool ON = false;
+};
+template <>
+struct ShiftTw<GL> {
+    static constexpr bool ON = true;
+    // log2 of w_(2^l) as a power of two, l = 0..4
+    static constexpr int expo(int l, bool inv) {
+        return l == 0 ? 0 : l == 1 ? 96 : l == 2 ? (inv ? 144 : 48) : l == 3 ? (inv ? 72 : 120) : (inv ? 36 : 156);
+    }
+};
+// x arrives canonical in stage 0 (loaded from HBM or just multiplied), lazy afterwards
+template <int E, bool X_CANON>
+MS_HD void gl_shift_butterfly(uint64_t& y, uint64_t& x) {
+    using A = Fast<GL>;
+    constexpr int e = E % 96;
+    uint64_t t;
+    if constexpr (e == 0) t = X_CANON ? x : A::canon(x);
+    else t = A::template mulpow2<e>(x);
+    const uint64_t u = y;
+    if constexpr (E < 96) { y = A::add(u, t); x = A::sub(u, t); }
+    else { y = A::sub(u, t); x = A::add(u, t); }
+}
+template <int G, bool INV, int ST, int R>
+MS_HD void gl_shift_dft_steps(uint64_t* v) {
+    if constexpr (ST < G) {
+        if constexpr (R < (1 << G)) {
+            if constexpr (!(R & (1 << ST))) {
+                constexpr int j = R & ((1 << ST) - 1);
+                constexpr int E = (ShiftTw<GL>::expo(ST + 1, INV) * j) % 192;
+                gl_shift_butterfly<E, ST == 0>(v[R], v[R | (1 << ST)]);
+            }
+            gl_shift_dft_steps<G, INV, ST, R + 1>(v);
+        } else {
+            gl_shift_dft_steps<G, INV, ST + 1, 0>(v);
+        }
+    }
+}
+// v[r], r odd, canonical on entry (stage 0 operands); every output lazy
+template <int G, bool INV>
+MS_HD void gl_shift_dft(uint64_t* v) {
+    static_assert(G >= 0 && G <= 4, "w_32 and w_64 are powers of two as well, but blocks stop at 16 elements");
+    gl_shift_dft_steps<G, INV, 0, 0>(v);
+}
+
+// ------------------------------------------------------------------------------------------------
 // twiddle tables (built on the device with the canonical field ops, stored in twiddle form)
 // ------------------------------------------------------------------------------------------------
 // plain DIT twiddles W[2^s + q] = g_(2^(s+1))^q, s < NTT_MAXLOG, g = (inverse) root of unity
@@ -255,6 +367,52 @@ __global__ void k_build_ft(typename F::T* ft, const typename F::T* shifts /*[B]*
     }
 }
 
+// Block twiddles of the fixed-shape Goldilocks kernel (ShiftTw): the round that starts at stage U and
+// spans G stages multiplies element r of the block at in-tile offset lo by beta^brev_G(r),
+//   beta = sigma^(2^(A-U-G)) * w_(2^(U+G))^lo        (sigma = the coset factor of the 2^A-point transform),
+// stored at tab[2^(U+G) + (n << U) + lo], n = brev_G(r) in [1, 2^G): the ranges of different rounds are
+// disjoint because U + G grows from round to round, so one coset needs 2^(A+1) entries.
+template <class F>
+struct TwRoots {
+    typename F::T w[NTT_MAXLOG + 1];  // w[l] = the (inverse) primitive 2^l-th root of unity
+};
+MS_HD int tile_rounds(int a);
+MS_HD int tile_round_size(int a, int r);
+template <class F>
+MS_HD typename F::T tw16_entry(uint32_t e, int A, typename F::T sigma, const TwRoots<F>& roots) {
+    using T = typename F::T;
+    if (e < 2) return 0;
+    int p = 0;
+    while ((2u << p) <= e) p++;  // p = floor(log2 e)
+    int U = 0, G = 0;
+    bool ok = false;
+    for (int r = 0; r < tile_rounds(A); r++) {
+        G = tile_round_size(A, r);
+        if (U + G == p) { ok = true; break; }
+        U += G;
+    }
+    if (!ok) return 0;
+    const uint32_t n = (e - (1u << p)) >> U, lo = e & ((1u << U) - 1);
+    T beta = fpow<F>(roots.w[p], (uint64_t)lo);
+    for (int i = 0; i < A - p; i++) sigma = F::mul(sigma, sigma);
+    beta = F::mul(beta, sigma);
+    return Fast<F>::to_tw(fpow<F>(beta, (uint64_t)n));
+}
+// sigma_j = shifts[j]^(2^log_n1) (pass 1 transforms x[m1 + n1 m2] s^(n1 m2) along m2); shifts == nullptr: 1
+template <class F>
+__global__ void k_build_tw16(typename F::T* tab, const typename F::T* shifts, TwRoots<F> roots, int A, int B, int log_n1) {
+    using T = typename F::T;
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((uint32_t)B << (A + 1))) return;
+    const uint32_t j = idx >> (A + 1), e = idx & ((2u << A) - 1);
+    T sigma = 1;
+    if (shifts) {
+        sigma = shifts[j];
+        for (int i = 0; i < log_n1; i++) sigma = F::mul(sigma, sigma);
+    }
+    tab[idx] = tw16_entry<F>(e, A, sigma, roots);
+}
+
 // ------------------------------------------------------------------------------------------------
 // the tile kernel
 // ------------------------------------------------------------------------------------------------
@@ -275,6 +433,7 @@ struct NttTile {
     uint32_t jmask, jstride;
     int mode;             // 0: first (or only) pass, 1: second pass
     int plain;            // tw is the plain table (no coset factors): twiddles with q = 0 are exactly 1
+    int inv;              // inverse transform (selects the power-of-two twiddles of the Goldilocks blocks)
     int bq;               // mode 0: log2(n1), the input stride of one transform step
     int cs;               // mode 0: coset-split bits: tile = (m1 << cs) | sub, coset j = (sub << beta) | b (then R = 1)
     int a1, beta1, logR1; // mode 1: geometry of the first pass (a1 = log2 n2)
@@ -475,12 +634,13 @@ struct FixedSwz {
     static constexpr uint32_t MASK = (1u << K) - 1;
 };
 
-template <class F, int A, int BETA, int R, int THREADS>
+template <class F, int A, int BETA, int R, int THREADS, bool INV>
 MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::T* __restrict__ src,
                        typename F::T* __restrict__ dst, uint32_t tile, uint32_t tid) {
     using T = typename F::T;
     using Ar = Fast<F>;
     using SW = FixedSwz<F, A, BETA>;
+    constexpr bool SHIFT = ShiftTw<F>::ON;  // g.tw is then the block-twiddle table (tw16_entry)
     constexpr int G = Rounds<A>::size(R), U = Rounds<A>::start(R), E = 1 << G;
     constexpr bool FIRST = R == 0, LAST = R == Rounds<A>::NR - 1;
     constexpr uint32_t NSLOTS = 1u << (A - G + BETA);
@@ -492,10 +652,18 @@ MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::
         const uint32_t P0 = lo | (hi << (U + G));
         const T* __restrict__ twj = g.tw + (size_t)(tile_coset<F>(g, tile, b) & g.jmask) * g.jstride + lo;
         T w[E];
+        if constexpr (SHIFT) {
+            // w[n] = beta^n, the factor of the element with sub-index n = brev_G(r); none in a plain first round
+            if (!(FIRST && g.plain)) {
 #pragma unroll
-        for (int st = 0; st < G; st++)
+                for (int n = 1; n < E; n++) w[n] = MS_LDG(&twj[(1u << (U + G)) + ((uint32_t)n << U)]);
+            }
+        } else {
 #pragma unroll
-            for (int r = 0; r < (1 << st); r++) w[(1 << st) + r] = MS_LDG(&twj[(1u << (U + st)) + ((uint32_t)r << U)]);
+            for (int st = 0; st < G; st++)
+#pragma unroll
+                for (int r = 0; r < (1 << st); r++) w[(1 << st) + r] = MS_LDG(&twj[(1u << (U + st)) + ((uint32_t)r << U)]);
+        }
         T v[E];
         if (FIRST) {
             // element r sits at position P0 + r whose bit reversal is brev(P0) | brev_G(r) << (A - G)
@@ -522,7 +690,13 @@ MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::
                 v[r] = S[((((Pb ^ cr) << BETA) | b)) + ((uint32_t)r << (U + BETA))];
             }
         }
-        if (FIRST && g.plain) {
+        if constexpr (SHIFT) {
+            if (!(FIRST && g.plain)) {
+#pragma unroll
+                for (int r = 1; r < E; r++) v[r] = Ar::mul(v[r], w[cbrev(r, G)]);
+            }
+            gl_shift_dft<G, INV>(v);
+        } else if (FIRST && g.plain) {
             // U == 0 and plain twiddles: w[2^st + 0] = 1, so those butterflies need no product, only
             // a canonical operand (the loaded values are canonical already: stage 0 needs nothing)
 #pragma unroll
@@ -590,17 +764,17 @@ MS_HD void fixed_round(const NttTile<F>& g, typename F::T* S, const typename F::
     }
 }
 
-template <class F, int A, int BETA, int R, int THREADS>
+template <class F, int A, int BETA, int R, int THREADS, bool INV>
 __device__ __forceinline__ void fixed_rounds_from(const NttTile<F>& g, typename F::T* S, const typename F::T* src,
                                                   typename F::T* dst, uint32_t tile) {
     if constexpr (R < Rounds<A>::NR) {
         if (R) __syncthreads();
-        fixed_round<F, A, BETA, R, THREADS>(g, S, src, dst, tile, threadIdx.x);
-        fixed_rounds_from<F, A, BETA, R + 1, THREADS>(g, S, src, dst, tile);
+        fixed_round<F, A, BETA, R, THREADS, INV>(g, S, src, dst, tile, threadIdx.x);
+        fixed_rounds_from<F, A, BETA, R + 1, THREADS, INV>(g, S, src, dst, tile);
     }
 }
 
-template <class F, int A, int BETA, int THREADS, int MINB>
+template <class F, int A, int BETA, int THREADS, int MINB, bool INV>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_ntt_fixed(const NttTile<F> g) {
     using T = typename F::T;
@@ -609,7 +783,7 @@ k_ntt_fixed(const NttTile<F> g) {
     T* S = reinterpret_cast<T*>(smem_raw);
     uint32_t col, tile;
     tile_of_block<F>(g, blockIdx.x, &col, &tile);
-    fixed_rounds_from<F, A, BETA, 0, THREADS>(g, S, g.src + (uint64_t)col * g.src_stride, g.dst + (uint64_t)col * g.dst_stride, tile);
+    fixed_rounds_from<F, A, BETA, 0, THREADS, INV>(g, S, g.src + (uint64_t)col * g.src_stride, g.dst + (uint64_t)col * g.dst_stride, tile);
 }
 
 template <class F>
@@ -706,14 +880,26 @@ inline bool ntt_plan(int logN, int logB, NttPlan* p) {
     return true;
 }
 
+// tile shapes with a compile-time specialisation
+#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0)
+// does launch_tile run this tile through k_ntt_fixed (and, for Goldilocks, with block twiddles)?
+template <class F>
+inline bool tile_is_fixed(const NttTile<F>& g) {
+    if (!(g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0))) return false;
+#define X(A_, B_) if (g.a == A_ && g.beta == B_) return true;
+    MS_NTT_FIXED_SHAPES(X)
+#undef X
+    return false;
+}
+
 #ifndef MS_NTT_NO_HOST
-template <class F, int A, int BETA>
-int launch_fixed(Ctx* c, const NttTile<F>& g, const char* name) {
+template <class F, int A, int BETA, bool INV>
+int launch_fixed_dir(Ctx* c, const NttTile<F>& g, const char* name) {
     using T = typename F::T;
     constexpr size_t smem = sizeof(T) << (A + BETA);
     constexpr bool big = smem > 100 * 1024;  // one CTA per SM: give it 512 threads
     constexpr int threads = big ? 512 : 256;
-    auto kern = k_ntt_fixed<F, A, BETA, threads, big ? 1 : MS_NTT_MINB>;
+    auto kern = k_ntt_fixed<F, A, BETA, threads, big ? 1 : MS_NTT_MINB, INV>;
     MS_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(c, name);
     kern<<<g.cols * g.tiles, threads, smem, c->stream>>>(g);
@@ -721,14 +907,49 @@ int launch_fixed(Ctx* c, const NttTile<F>& g, const char* name) {
     MS_LAUNCH_CHECK(c);
     return MS_OK;
 }
+template <class F, int A, int BETA>
+int launch_fixed(Ctx* c, const NttTile<F>& g, const char* name) {
+    // only the Goldilocks blocks depend on the direction (power-of-two twiddles are compiled in)
+    if constexpr (ShiftTw<F>::ON) {
+        if (g.inv) return launch_fixed_dir<F, A, BETA, true>(c, g, name);
+    }
+    return launch_fixed_dir<F, A, BETA, false>(c, g, name);
+}
 
-// tile shapes with a compile-time specialisation
-#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0)
+// block-twiddle table (tw16_entry) of a 2^a-point transform: per coset when `d_shifts` is given (then the
+// caller owns `own`), else the plain table of this direction, built once per context
+template <class F>
+int get_tw16(Ctx* c, int a, bool inverse, const typename F::T* d_shifts, int B, int log_n1, Scratch* own, const typename F::T** out) {
+    using T = typename F::T;
+    TwRoots<F> roots{};
+    for (int l = 0; l <= NTT_MAXLOG; l++) {
+        T g = (l <= F::TWO_ADICITY) ? root_of_unity<F>(l) : (T)1;
+        roots.w[l] = inverse ? finv<F>(g) : g;
+    }
+    T* tab;
+    if (d_shifts) {
+        MS_TRY(own->alloc(((size_t)B << (a + 1)) * sizeof(T)));
+        tab = own->template as<T>();
+    } else {
+        void*& slot = c->tw16_plain[inverse ? 1 : 0][a];
+        if (slot) { *out = reinterpret_cast<const T*>(slot); return MS_OK; }
+        MS_CUDA(c, cudaMalloc(&slot, ((size_t)2 << a) * sizeof(T)));
+        tab = reinterpret_cast<T*>(slot);
+        B = 1;
+    }
+    const unsigned n = (unsigned)B << (a + 1);
+    prof_begin(c, "k_build_tw16");
+    k_build_tw16<F><<<(n + 127) / 128, 128, 0, c->stream>>>(tab, d_shifts, roots, a, B, log_n1);
+    prof_end(c);
+    MS_LAUNCH_CHECK(c);
+    *out = tab;
+    return MS_OK;
+}
 
 template <class F>
 int launch_tile(Ctx* c, const NttTile<F>& g, const char* name) {
     using T = typename F::T;
-    if (g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0)) {
+    if (tile_is_fixed<F>(g)) {
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) return launch_fixed<F, A_, B_>(c, g, name);
         MS_NTT_FIXED_SHAPES(X)
 #undef X
@@ -782,10 +1003,26 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         sj = F::mul(sj, wL);
     }
     Scratch consts(c), t1(c), ft(c), tmp(c);
+    // geometry of the first pass decides which kernel runs it, and with it the twiddle-table format
+    NttTile<F> g1{};
+    g1.a = pl.a;
+    g1.beta = pl.beta1;
+    g1.cs = pl.cs1;
+    g1.logB = logB;
+    g1.mode = 0;
+    g1.inv = inverse ? 1 : 0;
+    const bool blocks1 = ShiftTw<F>::ON && tile_is_fixed<F>(g1);  // Goldilocks fixed-shape kernel: block twiddles
     const T* d_tw1 = wtab;
-    if (!plain) {
+    if (!plain || two) {  // per-coset constants (the shifts are also needed by k_build_ft)
         MS_TRY(consts.alloc(hbuf.size() * sizeof(T)));
         MS_CUDA(c, cudaMemcpyAsync(consts.p, hbuf.data(), hbuf.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    }
+    const T* d_shifts = consts.p ? consts.as<T>() + (size_t)B * na : nullptr;
+    uint32_t jstride1 = plain ? 0u : (1u << pl.a);
+    if (blocks1) {
+        MS_TRY(get_tw16<F>(c, pl.a, inverse, plain ? nullptr : d_shifts, B, pl.b, &t1, &d_tw1));
+        jstride1 = plain ? 0u : (2u << pl.a);
+    } else if (!plain) {
         MS_TRY(t1.alloc(((size_t)B << pl.a) * sizeof(T)));
         int n = B << pl.a;
         prof_begin(c, "k_build_t1");
@@ -797,11 +1034,6 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     const bool inplace = two && pl.logR1 == 0 && tile_rounds(pl.b) >= 2;
     const int lay1 = pl.logR1 + logB;  // low index bits (m1 offset, coset) of the intermediate layout
     if (two) {
-        if (plain) {  // the shifts are still needed by k_build_ft
-            MS_TRY(consts.alloc(hbuf.size() * sizeof(T)));
-            MS_CUDA(c, cudaMemcpyAsync(consts.p, hbuf.data(), hbuf.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-        }
-        const T* d_shifts = consts.as<T>() + (size_t)B * na;
         MS_TRY(ft.alloc(((size_t)N << logB) * sizeof(T)));
         int chunk_log = pl.a < 6 ? pl.a : 6;
         uint64_t threads = (((uint64_t)1 << pl.b) << logB) * ((1ULL << pl.a) >> chunk_log);
@@ -812,7 +1044,6 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         MS_LAUNCH_CHECK(c);
         if (!inplace) MS_TRY(tmp.alloc(cols * ((size_t)N << logB) * sizeof(T)));
     }
-    NttTile<F> g1{};
     g1.src = d_in;
     g1.src_stride = in_stride;
     g1.dst = two ? (inplace ? d_out : tmp.as<T>()) : d_out;
@@ -826,8 +1057,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     g1.cs = pl.cs1;
     g1.logB = logB;
     g1.jmask = plain ? 0u : (uint32_t)(B - 1);
-    g1.jstride = plain ? 0u : (1u << pl.a);
-    g1.mode = 0;
+    g1.jstride = jstride1;
     g1.plain = plain ? 1 : 0;
     g1.bq = pl.b;
     g1.tiles = (uint32_t)(((1ULL << pl.b) >> pl.logR1) << pl.cs1);
@@ -839,7 +1069,6 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         g2.src_stride = g1.dst_stride;
         g2.dst = d_out;
         g2.dst_stride = out_stride;
-        g2.tw = wtab;
         g2.ft = nullptr;
         g2.scale = 0;
         g2.has_scale = 0;
@@ -855,6 +1084,9 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         g2.logR1 = pl.logR1;
         g2.tiles = (uint32_t)(((1ULL << pl.a) << logB) >> pl.beta2);
         g2.cols = (uint32_t)cols;
+        g2.inv = inverse ? 1 : 0;
+        g2.tw = wtab;
+        if (ShiftTw<F>::ON && tile_is_fixed<F>(g2)) MS_TRY(get_tw16<F>(c, pl.b, inverse, nullptr, 1, 0, nullptr, &g2.tw));
         MS_TRY(launch_tile<F>(c, g2, "k_ntt_tile/pass2"));
     }
     return MS_OK;
@@ -862,16 +1094,27 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
 
 // Device self-test of the butterfly arithmetic against the canonical host ops (edge values first,
 // then xorshift-random operands): returns the number of mismatching (a, b) pairs.
+constexpr int SELFTEST_SHIFTS[] = {1, 12, 24, 31, 32, 36, 48, 60, 63, 64, 72, 84, 95};
+constexpr int SELFTEST_NSHIFT = sizeof(SELFTEST_SHIFTS) / sizeof(int);
+constexpr int SELFTEST_OUT = 4 + SELFTEST_NSHIFT;
+template <class F, int I>
+__device__ void selftest_shifts(typename F::T a, typename F::T* out) {
+    if constexpr (ShiftTw<F>::ON && I < SELFTEST_NSHIFT) {
+        out[4 + I] = Fast<F>::template mulpow2<SELFTEST_SHIFTS[I]>(a);
+        selftest_shifts<F, I + 1>(a, out);
+    }
+}
 template <class F>
 __global__ void k_selftest_ops(const typename F::T* a, const typename F::T* b, typename F::T* out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     using A = Fast<F>;
     typename F::T m = A::mul(a[i], A::to_tw(b[i]));
-    out[4 * i] = m;
-    out[4 * i + 1] = A::add(a[i], m);
-    out[4 * i + 2] = A::sub(a[i], m);
-    out[4 * i + 3] = A::canon(a[i]);
+    out[SELFTEST_OUT * i] = m;
+    out[SELFTEST_OUT * i + 1] = A::add(a[i], m);
+    out[SELFTEST_OUT * i + 2] = A::sub(a[i], m);
+    out[SELFTEST_OUT * i + 3] = A::canon(a[i]);
+    selftest_shifts<F, 0>(a[i], out + SELFTEST_OUT * i);  // Goldilocks: a * 2^S for the shifts above
 }
 template <class F>
 int selftest_ops(Ctx* c, uint64_t n_random, uint64_t* n_bad) {
@@ -898,12 +1141,12 @@ int selftest_ops(Ctx* c, uint64_t n_random, uint64_t* n_bad) {
     Scratch da(c), db(c), dout(c);
     MS_TRY(da.alloc(n * sizeof(T)));
     MS_TRY(db.alloc(n * sizeof(T)));
-    MS_TRY(dout.alloc(4 * (size_t)n * sizeof(T)));
+    MS_TRY(dout.alloc(SELFTEST_OUT * (size_t)n * sizeof(T)));
     MS_CUDA(c, cudaMemcpyAsync(da.p, a.data(), n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     MS_CUDA(c, cudaMemcpyAsync(db.p, b.data(), n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     k_selftest_ops<F><<<(n + 255) / 256, 256, 0, c->stream>>>(da.as<T>(), db.as<T>(), dout.as<T>(), n);
     MS_LAUNCH_CHECK(c);
-    std::vector<T> out(4 * (size_t)n);
+    std::vector<T> out(SELFTEST_OUT * (size_t)n);
     MS_CUDA(c, cudaMemcpyAsync(out.data(), dout.p, out.size() * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
     uint64_t bad = 0;
@@ -911,9 +1154,16 @@ int selftest_ops(Ctx* c, uint64_t n_random, uint64_t* n_bad) {
         const uint64_t av = (uint64_t)a[i] % P, bv = (uint64_t)b[i];
         const uint64_t m = (uint64_t)(((unsigned __int128)av * bv) % P);
         const uint64_t ad = (uint64_t)(((unsigned __int128)av + m) % P), sb = (uint64_t)(((unsigned __int128)av + P - m) % P);
-        bool ok = (uint64_t)out[4 * i] == m && (uint64_t)out[4 * i + 1] % P == ad && (uint64_t)out[4 * i + 2] % P == sb &&
-                  (uint64_t)out[4 * i + 3] == av;
-        if (!lazy) ok = ok && (uint64_t)out[4 * i + 1] < P && (uint64_t)out[4 * i + 2] < P;
+        const T* o = &out[(size_t)SELFTEST_OUT * i];
+        bool ok = (uint64_t)o[0] == m && (uint64_t)o[1] % P == ad && (uint64_t)o[2] % P == sb && (uint64_t)o[3] == av;
+        if (!lazy) ok = ok && (uint64_t)o[1] < P && (uint64_t)o[2] < P;
+        if (ShiftTw<F>::ON) {
+            for (int k = 0; k < SELFTEST_NSHIFT; k++) {  // canonical a * 2^S, by repeated doubling
+                uint64_t want = av;
+                for (int d = 0; d < SELFTEST_SHIFTS[k]; d++) want = (uint64_t)(((unsigned __int128)want * 2) % P);
+                ok = ok && (uint64_t)o[4 + k] == want;
+            }
+        }
         bad += ok ? 0 : 1;
     }
     if (n_bad) *n_bad = bad;

@@ -31,11 +31,11 @@ static void run_tiles(const NttTile<F>& g, unsigned threads) {
     }
 }
 
-template <class F, int A, int BETA, int R>
+template <class F, int A, int BETA, int R, bool INV>
 static void emu_fixed_rounds(const NttTile<F>& g, typename F::T* S, const typename F::T* src, typename F::T* dst, uint32_t tile) {
     if constexpr (R < Rounds<A>::NR) {
-        for (uint32_t t = 0; t < 256; t++) fixed_round<F, A, BETA, R, 256>(g, S, src, dst, tile, t);
-        emu_fixed_rounds<F, A, BETA, R + 1>(g, S, src, dst, tile);
+        for (uint32_t t = 0; t < 256; t++) fixed_round<F, A, BETA, R, 256, INV>(g, S, src, dst, tile, t);
+        emu_fixed_rounds<F, A, BETA, R + 1, INV>(g, S, src, dst, tile);
     }
 }
 template <class F, int A, int BETA>
@@ -45,18 +45,52 @@ static void run_fixed(const NttTile<F>& g) {
     for (uint32_t bid = 0; bid < g.cols * g.tiles; bid++) {
         uint32_t col, tile;
         tile_of_block<F>(g, bid, &col, &tile);
-        emu_fixed_rounds<F, A, BETA, 0>(g, S.data(), g.src + (uint64_t)col * g.src_stride, g.dst + (uint64_t)col * g.dst_stride, tile);
+        const T* src = g.src + (uint64_t)col * g.src_stride;
+        T* dst = g.dst + (uint64_t)col * g.dst_stride;
+        if (g.inv) emu_fixed_rounds<F, A, BETA, 0, true>(g, S.data(), src, dst, tile);
+        else emu_fixed_rounds<F, A, BETA, 0, false>(g, S.data(), src, dst, tile);
     }
+}
+// the shapes the emulation runs through the fixed-shape body: the product's (MS_NTT_FIXED_SHAPES) plus small ones
+#define EMU_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(5, 2) X(6, 0) X(7, 3) X(5, 1) X(7, 1)
+template <class F>
+static bool emu_is_fixed(const NttTile<F>& g) {
+    if (!(g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0))) return false;
+#define X(A_, B_) if (g.a == A_ && g.beta == B_) return true;
+    EMU_FIXED_SHAPES(X)
+#undef X
+    return false;
 }
 static int g_fixed_used = 0;
 template <class F>
 static void run_any(const NttTile<F>& g) {
-    if (g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0)) {
+    if (emu_is_fixed<F>(g)) {
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) { g_fixed_used++; return run_fixed<F, A_, B_>(g); }
-        X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(5, 2) X(6, 0) X(7, 3) X(5, 1) X(7, 1)
+        EMU_FIXED_SHAPES(X)
 #undef X
     }
     run_tiles<F>(g, 64);
+}
+// host copy of get_tw16 / k_build_tw16 (csrc/ntt.cuh)
+template <class F>
+static std::vector<typename F::T> host_tw16(int a, bool inverse, const std::vector<typename F::T>* shifts, int B, int log_n1) {
+    using T = typename F::T;
+    TwRoots<F> roots{};
+    for (int l = 0; l <= NTT_MAXLOG; l++) {
+        T g = (l <= F::TWO_ADICITY) ? root_of_unity<F>(l) : (T)1;
+        roots.w[l] = inverse ? finv<F>(g) : g;
+    }
+    if (!shifts) B = 1;
+    std::vector<T> tab((size_t)B << (a + 1));
+    for (int j = 0; j < B; j++) {
+        T sigma = 1;
+        if (shifts) {
+            sigma = (*shifts)[j];
+            for (int i = 0; i < log_n1; i++) sigma = F::mul(sigma, sigma);
+        }
+        for (uint32_t e = 0; e < (2u << a); e++) tab[((size_t)j << (a + 1)) + e] = tw16_entry<F>(e, a, sigma, roots);
+    }
+    return tab;
 }
 
 // mirrors lde_batch (csrc/ntt.cuh) with host tables
@@ -118,15 +152,24 @@ static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, 
     g1.tw = t1.data(); g1.ft = two ? ft.data() : nullptr;
     g1.scale = Fast<F>::to_tw(scale); g1.has_scale = (!two && scale != 1) ? 1 : 0;
     g1.a = pl.a; g1.beta = pl.beta1; g1.cs = pl.cs1; g1.logB = logB;
-    g1.jmask = B - 1; g1.jstride = 1u << pl.a; g1.mode = 0; g1.bq = pl.b;
+    g1.jmask = B - 1; g1.jstride = 1u << pl.a; g1.mode = 0; g1.bq = pl.b; g1.inv = inverse ? 1 : 0;
     g1.tiles = (uint32_t)(((1ULL << pl.b) >> pl.logR1) << pl.cs1); g1.cols = (uint32_t)cols;
+    std::vector<T> tw16_1, tw16_2;
+    if (ShiftTw<F>::ON && emu_is_fixed<F>(g1)) {  // Goldilocks fixed-shape body: block twiddles (as lde_batch)
+        tw16_1 = host_tw16<F>(pl.a, inverse, &shifts, B, pl.b);
+        g1.tw = tw16_1.data(); g1.jstride = 2u << pl.a;
+    }
     run_any<F>(g1);
     if (two) {
         NttTile<F> g2{};
         g2.src = g1.dst; g2.src_stride = g1.dst_stride; g2.dst = out.data(); g2.dst_stride = N << logB;
         g2.tw = wtab.data(); g2.a = pl.b; g2.beta = pl.beta2; g2.logB = logB; g2.mode = 1; g2.plain = 1;
         g2.a1 = pl.a; g2.beta1 = pl.logR1 + logB; g2.logR1 = pl.logR1;
-        g2.tiles = (uint32_t)(((1ULL << pl.a) << logB) >> pl.beta2); g2.cols = (uint32_t)cols;
+        g2.tiles = (uint32_t)(((1ULL << pl.a) << logB) >> pl.beta2); g2.cols = (uint32_t)cols; g2.inv = inverse ? 1 : 0;
+        if (ShiftTw<F>::ON && emu_is_fixed<F>(g2)) {
+            tw16_2 = host_tw16<F>(pl.b, inverse, nullptr, 1, 0);
+            g2.tw = tw16_2.data();
+        }
         run_any<F>(g2);
     }
     return out;
