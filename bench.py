@@ -103,6 +103,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_name(args):
+    return (f"goldilocks coset-LDE 2^{args.log_rows} rows x {args.cols} cols blowup {args.blowup} per GPU "
+            f"(BASELINE headline shape; coefficients -> evaluations on shift*<w_L>)")
+
+
 def synth_coeffs(n, cols, seed):
     """poly-major [cols, n] canonical Goldilocks coefficients (NTT sweep treats all C
     columns as coefficient vectors)."""
@@ -140,8 +145,7 @@ def run_reference(args):
         "impl": "reference", "metric": "lde_melem_per_s", "value": val, "unit": "Melem/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"goldilocks coset-LDE 2^{args.log_rows} rows x {args.cols} cols blowup {B}",
-                   "sample": f"{cols} of {args.cols} columns per step"},
+        "config": {"workload": workload_name(args), "sample": f"{cols} of {args.cols} columns per step"},
         "cpu_baseline": {"value": val, "unit": "Melem/s", "cores": min(threads, cols), "kind": "port",
                          "sample": f"{cols} columns x 2^{args.log_rows} -> 2^{args.log_rows + int(np.log2(B))} per step, oracle port "
                                    "(reference is Rust; no toolchain in the image)"},
@@ -316,8 +320,7 @@ def run_ours(args):
             "metric": "lde_melem_per_s", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"goldilocks coset-LDE 2^{args.log_rows} rows x {C} cols blowup {B} per GPU "
-                                   f"(BASELINE headline shape; coefficients -> evaluations on shift*<w_L>)",
+            "config": {"workload": workload_name(args),
                        "l2": "inputs (N*C*8) + outputs (L*C*8) exceed the 126 MB L2; no flush between iterations",
                        "parallelism": f"{world} independent column shards"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

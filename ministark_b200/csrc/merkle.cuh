@@ -245,6 +245,43 @@ k_leaf_hash(const typename F::T* __restrict__ data, uint64_t stride, uint64_t wi
 
 // parent p = SHA256(child[p*k] .. child[p*k + k-1]); digests are 8 state words
 template <int K>
+__device__ __forceinline__ void node_hash_one(const uint32_t* children, uint32_t* parents, uint64_t p) {
+    const uint4* src = reinterpret_cast<const uint4*>(children + p * 8 * K);
+    uint32_t st[8];
+    sha256_init(st);
+#pragma unroll
+    for (int blk = 0; blk < K / 2; blk++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint4 v = src[blk * 4 + i];
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        sha256_compress(st, w);
+    }
+    sha256_compress_padblock<32u * K * 8u>(st);
+    uint4* o = reinterpret_cast<uint4*>(parents + p * 8);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+// The top of a tree in one launch: from a level of `lv` <= TOP_NODES digests down to `stop` digests, one CTA,
+// levels separated by __syncthreads (the ~log_k(lv) launches it replaces cost more than the hashing).
+// `nodes` points at the first digest of the starting level; the levels follow each other as in d_nodes.
+constexpr int TOP_THREADS = 512;
+constexpr uint64_t TOP_NODES = 4096;
+template <int K>
+__global__ void __launch_bounds__(TOP_THREADS)
+k_tree_top(uint32_t* nodes, uint64_t lv, uint64_t stop) {
+    uint64_t src = 0;
+    while (lv > stop) {
+        const uint64_t np = lv / K;
+        for (uint64_t p = threadIdx.x; p < np; p += TOP_THREADS) node_hash_one<K>(nodes + src * 8, nodes + (src + lv) * 8, p);
+        src += lv;
+        lv = np;
+        __syncthreads();
+    }
+}
+template <int K>
 __global__ void __launch_bounds__(256)
 k_node_hash(const uint32_t* __restrict__ children, uint32_t* __restrict__ parents, uint64_t n_parents) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,10 +327,30 @@ inline void digest_words_to_bytes(const uint32_t* w, uint8_t* out) {
     }
 }
 
-// levels above the first: d_nodes holds `n1` level-1 digests followed by room for every upper level
+// levels above the first: d_nodes holds `n1` level-1 digests followed by room for every upper level;
+// climbs until `stop` digests are left and returns their offset (in digests) through *top
+inline int merkle_climb(Ctx* c, uint32_t* d_nodes, uint64_t n1, uint64_t k, uint64_t stop, uint64_t* top);
 inline int merkle_upper_levels(Ctx* c, uint32_t* d_nodes, uint64_t n1, uint64_t k) {
+    uint64_t top = 0;
+    return merkle_climb(c, d_nodes, n1, k, 1, &top);
+}
+inline int merkle_climb(Ctx* c, uint32_t* d_nodes, uint64_t n1, uint64_t k, uint64_t stop, uint64_t* top) {
     uint64_t src = 0, lv = n1;
-    while (lv > 1) {
+    while (lv > stop) {
+        if (lv <= TOP_NODES) {  // the rest of the tree in one launch
+            uint32_t* base = d_nodes + src * 8;
+            prof_begin(c, "k_tree_top");
+            switch (k) {
+                case 2: k_tree_top<2><<<1, TOP_THREADS, 0, c->stream>>>(base, lv, stop); break;
+                case 4: k_tree_top<4><<<1, TOP_THREADS, 0, c->stream>>>(base, lv, stop); break;
+                case 8: k_tree_top<8><<<1, TOP_THREADS, 0, c->stream>>>(base, lv, stop); break;
+                default: k_tree_top<16><<<1, TOP_THREADS, 0, c->stream>>>(base, lv, stop); break;
+            }
+            prof_end(c);
+            MS_LAUNCH_CHECK(c);
+            while (lv > stop) { src += lv; lv /= k; }
+            break;
+        }
         uint64_t np = lv / k;
         const uint32_t* ch = d_nodes + src * 8;
         uint32_t* pa = d_nodes + (src + lv) * 8;
@@ -310,6 +367,7 @@ inline int merkle_upper_levels(Ctx* c, uint32_t* d_nodes, uint64_t n1, uint64_t 
         src += lv;
         lv = np;
     }
+    *top = src;
     return MS_OK;
 }
 
@@ -406,26 +464,9 @@ int merkle_subtree(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_
     MS_TRY(nodes.alloc(total * 32));
     uint32_t* d_nodes = nodes.as<uint32_t>();
     MS_TRY(merkle_leaf_level<F>(c, d_data, stride, width, deg, lpn, n1, d_nodes, gather));
-    // the same level-by-level climb as merkle_upper_levels, stopping at `rem` digests
+    // the same climb as merkle_upper_levels, stopping at `rem` digests
     uint64_t src = 0;
-    lv = n1;
-    while (lv > rem) {
-        uint64_t np = lv / k;
-        const uint32_t* ch = d_nodes + src * 8;
-        uint32_t* pa = d_nodes + (src + lv) * 8;
-        unsigned nb = (unsigned)((np + 255) / 256);
-        prof_begin(c, "k_node_hash");
-        switch (k) {
-            case 2: k_node_hash<2><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
-            case 4: k_node_hash<4><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
-            case 8: k_node_hash<8><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
-            default: k_node_hash<16><<<nb, 256, 0, c->stream>>>(ch, pa, np); break;
-        }
-        prof_end(c);
-        MS_LAUNCH_CHECK(c);
-        src += lv;
-        lv = np;
-    }
+    MS_TRY(merkle_climb(c, d_nodes, n1, k, rem, &src));
     (void)full;
     MS_CUDA(c, cudaMemcpyAsync(d_out, d_nodes + src * 8, rem * 32, cudaMemcpyDeviceToDevice, c->stream));
     if (n_out) *n_out = rem;
