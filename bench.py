@@ -64,7 +64,8 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "utilization.gpu")
 
     def __init__(self, device: int):
         self.device = device
@@ -72,7 +73,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -87,7 +88,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, busy = [], [], set(), []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -96,11 +97,16 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                busy.append(float(f[9]) > 0)
+            except (ValueError, IndexError):
+                busy.append(True)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        under_load = [v for v, b in zip(sm, busy) if b] or sm  # samples taken while the GPU was busy
+        return {"sm_mhz": float(np.median(under_load)) if under_load else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_under_load": len(under_load), "reasons": sorted(reasons)}
 
 
 def workload_name(args):
@@ -205,7 +211,8 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0
     kern = ctx.profile_collect()
     ctx.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
+    # the sampler keeps running through the e2e section below (GPU busy throughout), so that the median is taken
+    # over a dozen samples under load instead of the one or two that fit the 50 ms LDE region
     t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{dev}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -237,6 +244,7 @@ def run_ours(args):
                "call": "ms_coset_lde_host (pinned host buffers, row-major evaluations out)"}
         del h_in, h_out
 
+    clocks = sampler.stop() if rank == 0 else None  # window = the LDE and e2e regions (GPU busy throughout)
     # ---- full prove on the same shape -------------------------------------------------------------
     # N = 1: the plain prover.  N > 1: one replica per GPU with the trace tree and the LDE + its tree
     # sharded (ministark_b200/sharded.py): strong scaling of one proof, max over ranks.

@@ -294,6 +294,8 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     pw.u64(R - 1);
     struct PendingCopy { uint64_t at; const void* src; size_t bytes; };
     std::vector<PendingCopy> copies;
+    cudaEvent_t dl[2] = {nullptr, nullptr};  // first / last proof-download copy on the copy stream (timing only)
+    uint64_t dl_bytes = 0;
     for (uint64_t i = 0; i + 1 < R; i++) {
         FriRoundDev<F>& prev = rounds[i];
         FriRoundDev<F>& nxt = rounds[i + 1];
@@ -396,12 +398,28 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         if (!copies.empty()) {
             MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
             MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
-            for (auto& cp : copies)
+            if (!dl[0]) {
+                cudaEventCreate(&dl[0]);
+                cudaEventCreate(&dl[1]);
+                cudaEventRecord(dl[0], c->copy_stream);
+            }
+            for (auto& cp : copies) {
                 MS_CUDA(c, cudaMemcpyAsync(proof_out + cp.at, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+                dl_bytes += cp.bytes;
+            }
             copies.clear();
         }
     }
+    if (dl[0]) cudaEventRecord(dl[1], c->copy_stream);
     MS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    if (dl[0]) {
+        float ms_ = 0;
+        cudaEventElapsedTime(&ms_, dl[0], dl[1]);
+        ps->timings.emplace_back("(proof download, copy stream)", ms_);
+        ps->timings.emplace_back("(proof download GB)", (float)(dl_bytes * 1e-9));
+        cudaEventDestroy(dl[0]);
+        cudaEventDestroy(dl[1]);
+    }
     if (!pw.fits()) {
         *proof_len = pw.pos;
         return fail(c, MS_ERR_BUFFER_TOO_SMALL, "proof buffer needs %llu bytes", (unsigned long long)pw.pos);
