@@ -250,7 +250,7 @@ def run_ours(args):
     # sharded (ministark_b200/sharded.py): strong scaling of one proof, max over ranks.
     prove = None
     if not args.no_prove:
-        from ministark_b200.sharded import stark_prove_sharded
+        from ministark_b200.sharded import SharedProofBuffer, stark_prove_sharded
         from tests.synth import synth_linear_matrix, synth_trace
 
         W = C // 2
@@ -259,7 +259,12 @@ def run_ours(args):
         m = synth_linear_matrix(GL, n, W)
         params = StarkParams(args.security_bits, B, steps, C, 2)
         bound = int(ctx.lib.ms_stark_proof_bound(GL, params, n, C))
-        proof_buf = torch.empty(bound, dtype=torch.uint8).pin_memory().numpy()
+        shared = None
+        if world > 1:  # one shared host buffer: every rank downloads 1/world of the quotient polynomials
+            shared = SharedProofBuffer(ctx, bound, dist)
+            proof_buf = shared.array
+        else:
+            proof_buf = torch.empty(bound, dtype=torch.uint8).pin_memory().numpy()
         trace_cm = ctx.to_device(np.ascontiguousarray(trace_rm.T))
         torch.cuda.synchronize()
         ms_dev, ms_host, plen, stages = [], [], 0, None
@@ -267,7 +272,7 @@ def run_ours(args):
             barrier()
             t0 = time.perf_counter()
             if world > 1:
-                plen = stark_prove_sharded(ctx, params, trace_cm, m, proof_buf, dist)
+                plen = stark_prove_sharded(ctx, params, trace_cm, m, shared, dist)
             else:
                 plen = ctx.stark_prove_device(params, trace_cm, m, proof_buf)
             torch.cuda.synchronize()
@@ -295,12 +300,15 @@ def run_ours(args):
 
         prove = {"prove_ms": float(np.mean(ms_dev)), "prove_e2e_ms": float(np.mean(ms_host)) if ms_host else None,
                  "proof_bytes": plen, "proof_sha256": hashlib.sha256(proof_buf[:plen].tobytes()).hexdigest(),
-                 "scaling": "strong (one proof; commitments sharded over the ranks, FRI replicated)" if world > 1 else "single GPU",
+                 "scaling": "strong (one proof; commitments and the proof download sharded over the ranks, FRI replicated)" if world > 1 else "single GPU",
                  "config": f"SynthLinear AIR W={W} T={W} (C={C}), N=2^{args.log_rows}, blowup {B}, security {args.security_bits} bits, binary trees",
                  "stages_ms": {k: round(v, 3) for k, v in (stages or [])}}
         if world > 1:
             prove["sharded"] = getattr(ctx, "last_sharded_stats", None)
         del trace_cm
+        if shared is not None:
+            del proof_buf
+            shared.close()
 
     # ---- CPU baseline (rank 0): the oracle port, single thread, bounded sample ---------------------
     cpu = None

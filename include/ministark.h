@@ -188,6 +188,13 @@ typedef struct ms_commit_hooks {
      * the proof bytes, src/fri.rs:167 -- are not downloaded (N simultaneous multi-GB PCIe reads would
      * only slow rank 0 down).  proof_out then holds the fixed part and *proof_len the full length. */
     int32_t replica_only;
+    /* Sharded proof download (download_world > 1): proof_out is then ONE host buffer shared by all ranks
+     * (e.g. POSIX shared memory, page-locked in every process with ms_host_register).  Every replica holds the
+     * same quotient polynomials, so rank r downloads only every download_world-th of them (r, r + world, ...)
+     * over its own PCIe link, each to its final offset; rank 0 also writes the fixed part.  The caller adds a
+     * barrier after the call.  replica_only is ignored in this mode. */
+    int32_t download_rank;
+    int32_t download_world;
 } ms_commit_hooks;
 /* ms_stark_prove_device with the two commitments routed through `hooks` (NULL members = local). */
 int32_t ms_stark_prove_hooked(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
@@ -222,6 +229,11 @@ int32_t ms_peer_free(ms_ctx* ctx, void* d_ptr);
 int32_t ms_peer_export(ms_ctx* ctx, void* d_ptr, uint8_t* handle64);
 int32_t ms_peer_open(ms_ctx* ctx, const uint8_t* handle64, void** d_out);
 int32_t ms_peer_close(ms_ctx* ctx, void* d_ptr);
+
+/* Page-lock / unlock caller-owned host memory (cudaHostRegister) so that downloads into it run at PCIe speed;
+ * used for the shared proof buffer of the sharded download. */
+int32_t ms_host_register(ms_ctx* ctx, void* host_ptr, uint64_t bytes);
+int32_t ms_host_unregister(ms_ctx* ctx, void* host_ptr);
 
 /* per-stage device times (ms) of the last ms_stark_prove* call: fills up to `cap` entries, returns count.
  * names[i] points to static strings. */

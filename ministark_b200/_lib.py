@@ -32,7 +32,7 @@ LDE_COMMIT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_u
 class CommitHooks(C.Structure):
     """ms_commit_hooks (include/ministark.h)"""
     _fields_ = [("user", C.c_void_p), ("trace_commit", TRACE_COMMIT_FN), ("lde_commit", LDE_COMMIT_FN),
-                ("replica_only", C.c_int32)]
+                ("replica_only", C.c_int32), ("download_rank", C.c_int32), ("download_world", C.c_int32)]
 
 
 # every symbol include/ministark.h declares: name -> (restype, argtypes)
@@ -78,6 +78,8 @@ SIGNATURES = {
     "ms_peer_export": (_i32, [_vp, _vp, _vp]),
     "ms_peer_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
     "ms_peer_close": (_i32, [_vp, _vp]),
+    "ms_host_register": (_i32, [_vp, _vp, _u64]),
+    "ms_host_unregister": (_i32, [_vp, _vp]),
     "ms_stark_last_timings": (_i32, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i32]),
 }
 

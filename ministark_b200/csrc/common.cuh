@@ -24,6 +24,11 @@ struct Ctx {
     void* wtab[2] = {nullptr, nullptr};  // plain DIT twiddles, forward / inverse (see ntt.cuh)
     void* tw16_plain[2][16] = {};        // plain block-twiddle tables per direction and transform size (ntt.cuh)
     uint32_t* dec4 = nullptr;            // ASCII of 4-digit groups (see merkle.cuh)
+    // small results that the host needs while the copy engine is busy with the proof download: kernels store
+    // them straight into mapped pinned memory (no D2H copy that would queue behind the multi-MB transfers)
+    uint8_t* hstage = nullptr;           // host address
+    uint8_t* hstage_dev = nullptr;       // the same memory as seen from the device
+    size_t hstage_bytes = 0;
     unsigned long long launches = 0;     // kernels launched by this library (bench gpu_launches)
     // optional per-kernel device timing (bench.py roofline): event pairs collected by ms_profile_collect
     bool profile = false;
@@ -102,6 +107,28 @@ inline void prof_begin(Ctx* c, const char* name) {
 inline void prof_end(Ctx* c) {
     if (!c->profile || c->prof.empty()) return;
     cudaEventRecord(c->prof.back().b, c->stream);
+}
+
+__global__ void k_store_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+// queue "copy `bytes` (multiple of 4) from device memory to offset `off` of the mapped staging buffer" on the
+// stream; the host reads c->hstage + off after synchronising the stream
+inline int stage_to_host(Ctx* c, size_t off, const void* d_src, size_t bytes) {
+    if (!c->hstage) {
+        const size_t cap = 8u << 20;
+        MS_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->hstage), cap, cudaHostAllocMapped));
+        MS_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hstage_dev), c->hstage, 0));
+        c->hstage_bytes = cap;
+    }
+    if (off + bytes > c->hstage_bytes || (bytes & 3) || (off & 3)) return fail(c, MS_ERR_UNSUPPORTED, "staging buffer too small (%zu + %zu bytes)", off, bytes);
+    const uint64_t n = bytes / 4;
+    if (n == 0) return MS_OK;
+    k_store_words<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->hstage_dev + off),
+                                                                     reinterpret_cast<const uint32_t*>(d_src), n);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
 }
 
 inline int ilog2(uint64_t v) {

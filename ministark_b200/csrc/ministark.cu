@@ -120,6 +120,7 @@ void ms_ctx_destroy(ms_ctx* c) {
         for (int a = 0; a < 16; a++)
             if (c->tw16_plain[i][a]) cudaFree(c->tw16_plain[i][a]);
     if (c->dec4) cudaFree(c->dec4);
+    if (c->hstage) cudaFreeHost(c->hstage);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->copy_event) cudaEventDestroy(c->copy_event);
     delete c->prover;
@@ -363,6 +364,15 @@ int32_t ms_peer_open(ms_ctx* c, const uint8_t* handle64, void** d_out) {
 }
 int32_t ms_peer_close(ms_ctx* c, void* d_ptr) {
     if (d_ptr) MS_CUDA(c, cudaIpcCloseMemHandle(d_ptr));
+    return MS_OK;
+}
+int32_t ms_host_register(ms_ctx* c, void* host_ptr, uint64_t bytes) {
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return MS_OK;
+}
+int32_t ms_host_unregister(ms_ctx* c, void* host_ptr) {
+    MS_CUDA(c, cudaHostUnregister(host_ptr));
     return MS_OK;
 }
 int32_t ms_merkle_reduce(ms_ctx* c, const uint32_t* d_digests, uint64_t n, uint64_t k, uint8_t* root32) {

@@ -4,6 +4,7 @@
 // field elements, and at the very end the proof (whose size is dominated by the per-query FRI
 // quotient polynomials the reference puts in it, fri.rs:167).
 #pragma once
+#include <chrono>
 #include <utility>
 
 #include "common.cuh"
@@ -54,9 +55,10 @@ struct StageTimer {
 struct ProofWriter {
     uint8_t* out;
     uint64_t cap, pos = 0;
+    bool mute = false;  // advance only (another rank writes these bytes into the shared buffer)
     ProofWriter(uint8_t* o, uint64_t c) : out(o), cap(c) {}
     void bytes(const void* p, size_t n) {
-        if (out && pos + n <= cap) memcpy(out + pos, p, n);
+        if (out && !mute && pos + n <= cap) memcpy(out + pos, p, n);
         pos += n;
     }
     void u64(uint64_t v) { bytes(&v, 8); }  // little-endian host
@@ -277,7 +279,12 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     std::vector<uint64_t> betas(QF);
     for (uint64_t k = 0; k < QF; k++) memcpy(&betas[k], &braw[8 * k], 8);               // usize::from_le_bytes
     // ---- serialise the fixed part (field order of starks.rs:21-28)
+    // sharded download: every rank computes the same offsets, rank 0 alone writes the fixed part
+    const bool dl_sharded = hooks && hooks->download_world > 1;
+    const uint64_t dl_rank = dl_sharded ? (uint64_t)hooks->download_rank : 0, dl_world = dl_sharded ? (uint64_t)hooks->download_world : 1;
+    uint64_t copy_seq = 0;
     ProofWriter pw(proof_out, *proof_len);
+    pw.mute = dl_sharded && dl_rank != 0;
     pw.bytes("MSTARKP1", 8);
     pw.u32((uint32_t)F::ID);
     pw.u32((uint32_t)D);
@@ -296,7 +303,10 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     std::vector<PendingCopy> copies;
     cudaEvent_t dl[2] = {nullptr, nullptr};  // first / last proof-download copy on the copy stream (timing only)
     uint64_t dl_bytes = 0;
+    double q_host[4] = {0, 0, 0, 0};  // wall ms: look-ups + value search | neighbours, paths, quotients | serialise | enqueue copies
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (uint64_t i = 0; i + 1 < R; i++) {
+        double t_q = now_ms();
         FriRoundDev<F>& prev = rounds[i];
         FriRoundDev<F>& nxt = rounds[i + 1];
         const uint64_t nd = prev.domain;
@@ -337,11 +347,17 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(prev.cw, prev.domain, nd, d_ys.as<E>(), (int)(2 * QF), d_found.as<unsigned long long>());
         MS_LAUNCH_CHECK(c);
         std::vector<unsigned long long> found(2 * QF);
-        MS_CUDA(c, cudaMemcpyAsync(ys.data(), d_ys.p, 3 * QF * sizeof(E), cudaMemcpyDeviceToHost, c->stream));
-        MS_CUDA(c, cudaMemcpyAsync(found.data(), d_found.p, 2 * QF * 8, cudaMemcpyDeviceToHost, c->stream));
+        // small results go through mapped pinned memory, not the copy engine: a D2H copy here would queue
+        // behind the previous rounds' multi-MB quotient downloads and serialise this loop with the download
+        const size_t ys_bytes = 3 * QF * sizeof(E), found_bytes = 2 * QF * 8;
+        MS_TRY(stage_to_host(c, 0, d_ys.p, ys_bytes));
+        MS_TRY(stage_to_host(c, ys_bytes, d_found.p, found_bytes));
         MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(ys.data(), c->hstage, ys_bytes);
+        memcpy(found.data(), c->hstage + ys_bytes, found_bytes);
         for (auto f : found)
             if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
+        q_host[0] += now_ms() - t_q; t_q = now_ms();
         const int path_len = ilog2(nd / 2);
         std::vector<unsigned long long> nidx(4 * QF);
         for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = found[k] & ~1ULL; nidx[2 * k + 1] = found[k] | 1ULL; }
@@ -356,10 +372,10 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             int total = (int)(2 * QF) * path_len * 16;
             k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(prev.nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
             MS_LAUNCH_CHECK(c);
-            MS_CUDA(c, cudaMemcpyAsync(paths.data(), d_paths.p, paths.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+            MS_TRY(stage_to_host(c, 4 * QF * sizeof(E), d_paths.p, paths.size() * 4));
         }
         std::vector<E> neigh(4 * QF);
-        MS_CUDA(c, cudaMemcpyAsync(neigh.data(), d_neigh.p, 4 * QF * sizeof(E), cudaMemcpyDeviceToHost, c->stream));
+        MS_TRY(stage_to_host(c, 0, d_neigh.p, 4 * QF * sizeof(E)));
         // quotients (fri.rs:157-167)
         const uint64_t nq = prev.len >= 3 ? prev.len - 2 : 0;
         T* d_quot = nullptr;
@@ -368,6 +384,9 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             MS_TRY(fri_query_quotients<F>(c, prev.poly, prev.npad, prev.len, s2.data(), (uint32_t)QF, d_quot));
         }
         MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(neigh.data(), c->hstage, 4 * QF * sizeof(E));
+        if (path_len) memcpy(paths.data(), c->hstage + 4 * QF * sizeof(E), paths.size() * 4);
+        q_host[1] += now_ms() - t_q; t_q = now_ms();
         // ---- serialise this round (fri.rs:18-22, merkle.rs:293-298)
         pw.u64(QF);
         for (uint64_t k = 0; k < QF; k++) {
@@ -389,12 +408,16 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
                 }
             }
             pw.u64(nq);
-            if (nq) copies.push_back({pw.reserve(nq * sizeof(E)), d_quot + (size_t)k * nq * D, (size_t)(nq * sizeof(E))});
+            if (nq) {
+                const uint64_t at = pw.reserve(nq * sizeof(E));
+                if (copy_seq++ % dl_world == dl_rank) copies.push_back({at, d_quot + (size_t)k * nq * D, (size_t)(nq * sizeof(E))});
+            }
         }
+        q_host[2] += now_ms() - t_q; t_q = now_ms();
         // The quotient polynomials are ~all of the proof bytes (fri.rs:167): start this round's download on
         // the copy stream now, so it overlaps the next rounds' kernels and host work (the proof buffer was
         // checked against the size bound up front, so every offset is in range).
-        if (hooks && hooks->replica_only) copies.clear();
+        if (hooks && hooks->replica_only && !dl_sharded) copies.clear();
         if (!copies.empty()) {
             MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
             MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
@@ -409,7 +432,12 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             }
             copies.clear();
         }
+        q_host[3] += now_ms() - t_q;
     }
+    ps->timings.emplace_back("(query host: look-ups + search)", (float)q_host[0]);
+    ps->timings.emplace_back("(query host: paths + quotients)", (float)q_host[1]);
+    ps->timings.emplace_back("(query host: serialise)", (float)q_host[2]);
+    ps->timings.emplace_back("(query host: enqueue copies)", (float)q_host[3]);
     if (dl[0]) cudaEventRecord(dl[1], c->copy_stream);
     MS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     if (dl[0]) {

@@ -330,7 +330,7 @@ class ShardedCommitter:
         return self.dist.get_global_rank(self.group, group_rank)
 
     # ---- ctypes glue
-    def hooks(self, replica_only: bool = False) -> "_lib.CommitHooks":
+    def hooks(self, replica_only: bool = False, download: Tuple[int, int] = (0, 0)) -> "_lib.CommitHooks":
         def _tc(_user, d_trace, n, w, root32):
             try:
                 root = self.trace_commit(int(d_trace), int(n), int(w))
@@ -351,26 +351,83 @@ class ShardedCommitter:
 
         self.error: Optional[Exception] = None
         self._cb = (_lib.TRACE_COMMIT_FN(_tc), _lib.LDE_COMMIT_FN(_lc))
-        return _lib.CommitHooks(None, self._cb[0], self._cb[1], 1 if replica_only else 0)
+        return _lib.CommitHooks(None, self._cb[0], self._cb[1], 1 if replica_only else 0, download[0], download[1])
 
 
-def stark_prove_sharded(ctx, params, trace_cm, constraint_matrix: np.ndarray, out: np.ndarray, dist=None, group=None,
+class SharedProofBuffer:
+    """One host buffer for the proof, visible to every rank of a node (POSIX shared memory) and page-locked in
+    every process, so that each rank can download its share of the quotient polynomials over its own PCIe
+    link straight to the final offsets (ms_commit_hooks.download_rank / download_world).  `array` is the
+    uint8 view; rank 0 reads the proof from it after stark_prove_sharded returns."""
+
+    def __init__(self, ctx, nbytes: int, dist, group=None):
+        from multiprocessing import shared_memory
+
+        self.ctx, self.dist, self.group = ctx, dist, group
+        rank = dist.get_rank(group)
+        names = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            names[0] = self.shm.name
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(names, src=src, group=group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=names[0])
+            try:  # the creator unlinks; keep the resource tracker of the other ranks from doing it again
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.owner = rank == 0
+        self.nbytes = nbytes
+        self.array = np.frombuffer(self.shm.buf, dtype=np.uint8, count=nbytes)
+        ctx._check(ctx.lib.ms_host_register(ctx.h, C.c_void_p(self.array.ctypes.data), nbytes))
+        self.registered = True
+        dist.barrier(group=group)
+
+    def close(self):
+        if getattr(self, "registered", False):
+            self.ctx.lib.ms_host_unregister(self.ctx.h, C.c_void_p(self.array.ctypes.data))
+            self.registered = False
+        self.dist.barrier(group=self.group)
+        arr, self.array = self.array, None
+        del arr
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        if self.owner:
+            self.shm.unlink()
+
+
+def stark_prove_sharded(ctx, params, trace_cm, constraint_matrix: np.ndarray, out, dist=None, group=None,
                         proof_on_all_ranks: bool = False) -> int:
     """Stark::prove on this rank's replica with the commitments sharded over the process group.
-    trace_cm: device [W, N] (every rank holds it); out: host uint8 buffer.  Returns the proof length.
-    Rank 0 holds the proof; with proof_on_all_ranks every rank downloads the (identical) bytes."""
+    trace_cm: device [W, N] (every rank holds it).  out: a host uint8 array -- rank 0 then downloads the
+    whole proof (the other ranks only with proof_on_all_ranks) -- or a SharedProofBuffer: every rank downloads
+    1/world of the quotient polynomials into the one shared buffer in parallel (the proof bytes are ~all
+    quotients, src/fri.rs:167, so the PCIe-bound tail of the proof shrinks by the number of GPUs).
+    Returns the proof length."""
     w, n = trace_cm.shape
     m = np.ascontiguousarray(constraint_matrix, dtype=ctx.np_dtype).reshape(-1, w)
     ops = getattr(ctx, "_sharded_ops", None)
     if ops is None:
         ops = ctx._sharded_ops = CudaOps(ctx)
     com = ShardedCommitter(ops, int(params.trace_columns), int(params.inner_children) or 2, dist, group)
-    hooks = com.hooks(replica_only=(com.rank != 0 and not proof_on_all_ranks))
-    cap = C.c_uint64(out.size)
+    shared = isinstance(out, SharedProofBuffer)
+    buf = out.array if shared else out
+    if shared and com.world > 1:
+        hooks = com.hooks(download=(com.rank, com.world))
+    else:
+        hooks = com.hooks(replica_only=(com.rank != 0 and not proof_on_all_ranks))
+    cap = C.c_uint64(buf.size)
     rc = ctx.lib.ms_stark_prove_hooked(ctx.h, C.byref(params), C.c_void_p(trace_cm.data_ptr()), n, w, m.ctypes.data, m.shape[0],
-                                       C.byref(hooks), out.ctypes.data, C.byref(cap))
+                                       C.byref(hooks), buf.ctypes.data, C.byref(cap))
     if com.error is not None:
         raise com.error
     ctx._check(rc)
+    if shared and com.world > 1:
+        dist.barrier(group=group)  # every rank's share has landed in the shared buffer
     ctx.last_sharded_stats = dict(com.stats)
     return int(cap.value)

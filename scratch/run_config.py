@@ -7,7 +7,7 @@ import numpy as np, torch
 sys.path.insert(0, '.')
 from ministark_b200 import Context
 from ministark_b200._lib import StarkParams
-from ministark_b200.sharded import stark_prove_sharded
+from ministark_b200.sharded import SharedProofBuffer, stark_prove_sharded
 from tests.synth import synth_linear_matrix, synth_trace
 
 logn, C, B, k = (int(x) for x in sys.argv[1:5])
@@ -26,7 +26,12 @@ trace_rm = synth_trace(0, n, W, seed=0x5EED000000000001)
 m = synth_linear_matrix(0, n, W)
 params = StarkParams(sec, B, n - 1, C, k)
 bound = int(ctx.lib.ms_stark_proof_bound(0, params, n, C))
-buf = torch.empty(bound, dtype=torch.uint8).pin_memory().numpy() if rank == 0 else np.empty(bound, dtype=np.uint8)  # replicas only write the fixed part
+shared_dl = world > 1 and os.environ.get('MINISTARK_DOWNLOAD', 'sharded') == 'sharded'
+if shared_dl:
+    shared = SharedProofBuffer(ctx, bound, dist)  # every rank downloads 1/world of the quotient polynomials
+    buf = shared.array
+else:
+    buf = torch.empty(bound, dtype=torch.uint8).pin_memory().numpy() if rank == 0 else np.empty(bound, dtype=np.uint8)  # replicas only write the fixed part
 trace_cm = ctx.to_device(np.ascontiguousarray(trace_rm.T))
 del trace_rm
 times, ln, stages = [], 0, None
@@ -34,7 +39,7 @@ for i in range(reps + 1):
     if dist: dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     if world > 1:
-        ln = stark_prove_sharded(ctx, params, trace_cm, m, buf, dist)
+        ln = stark_prove_sharded(ctx, params, trace_cm, m, shared if shared_dl else buf, dist)
     else:
         ln = ctx.stark_prove_device(params, trace_cm, m, buf)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
@@ -50,6 +55,10 @@ if rank == 0:
         "proof_bytes": ln, "proof_sha256": hashlib.sha256(buf[:ln].tobytes()).hexdigest(),
         "stages_ms": {a: round(b, 3) for a, b in (stages or [])},
         "sharded": getattr(ctx, "last_sharded_stats", None) if world > 1 else None,
+        "download": ("sharded over the ranks (shared host buffer)" if shared_dl else "rank 0") if world > 1 else "single GPU",
         "mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 2)}), flush=True)
+if shared_dl:
+    del buf
+    shared.close()
 if dist: dist.destroy_process_group()
 ctx.close()

@@ -207,9 +207,21 @@ def _nccl_worker(rank, world, port, log_n, w, blowup, k, q):
         trace = synth_trace(0, n, w, seed=123)
         m = synth_linear_matrix(0, n, w)
         params = StarkParams(40, blowup, n - 1, 2 * w, k)
-        out = np.empty(int(ctx.lib.ms_stark_proof_bound(0, params, n, 2 * w)), dtype=np.uint8)
-        ln = stark_prove_sharded(ctx, params, ctx.to_device(np.ascontiguousarray(trace.T)), m, out, dist, proof_on_all_ranks=True)
-        q.put((rank, hashlib.sha256(out[:ln].tobytes()).hexdigest()))
+        bound = int(ctx.lib.ms_stark_proof_bound(0, params, n, 2 * w))
+        d_trace = ctx.to_device(np.ascontiguousarray(trace.T))
+        if os.environ.get("MINISTARK_TEST_SHARED_DOWNLOAD") == "1":
+            # one shared host buffer, every rank downloads its share of the quotient polynomials
+            from ministark_b200.sharded import SharedProofBuffer
+
+            shared = SharedProofBuffer(ctx, bound, dist)
+            ln = stark_prove_sharded(ctx, params, d_trace, m, shared, dist)
+            digest = hashlib.sha256(shared.array[:ln].tobytes()).hexdigest()
+            shared.close()
+        else:
+            out = np.empty(bound, dtype=np.uint8)
+            ln = stark_prove_sharded(ctx, params, d_trace, m, out, dist, proof_on_all_ranks=True)
+            digest = hashlib.sha256(out[:ln].tobytes()).hexdigest()
+        q.put((rank, digest))
         ctx.close()
     finally:
         dist.destroy_process_group()
@@ -224,6 +236,8 @@ def test_sharded_prover_multi_gpu_equals_single(k, exchange, monkeypatch):
     import torch
 
     monkeypatch.setenv("MINISTARK_EXCHANGE", exchange)  # inherited by the spawned ranks
+    # the peer runs also exercise the sharded proof download (SharedProofBuffer)
+    monkeypatch.setenv("MINISTARK_TEST_SHARED_DOWNLOAD", "1" if exchange == "peer" else "0")
     import torch.multiprocessing as mp
 
     world = min(torch.cuda.device_count(), 4)
