@@ -287,7 +287,7 @@ def run_ours(args):
             h_trace = torch.from_numpy(trace_rm.view(np.int64)).pin_memory().numpy().view(np.uint64)
             import ctypes as Cc
 
-            for i in range(2):
+            for i in range(3):
                 cap = Cc.c_uint64(proof_buf.size)
                 t0 = time.perf_counter()
                 rc = ctx.lib.ms_stark_prove(ctx.h, Cc.byref(params), h_trace.ctypes.data, n, W, m.ctypes.data, W,

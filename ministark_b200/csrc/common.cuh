@@ -28,7 +28,8 @@ struct Ctx {
     // them straight into mapped pinned memory (no D2H copy that would queue behind the multi-MB transfers)
     uint8_t* hstage = nullptr;           // host address
     uint8_t* hstage_dev = nullptr;       // the same memory as seen from the device
-    size_t hstage_bytes = 0;
+    size_t hstage_bytes = 0;             // [0, HSTAGE_OUT): device -> host results; the rest: host -> device inputs
+    size_t hstage_in_used = 0;           // bump allocator over the input region, reset at stream syncs it forces
     unsigned long long launches = 0;     // kernels launched by this library (bench gpu_launches)
     // optional per-kernel device timing (bench.py roofline): event pairs collected by ms_profile_collect
     bool profile = false;
@@ -109,20 +110,45 @@ inline void prof_end(Ctx* c) {
     cudaEventRecord(c->prof.back().b, c->stream);
 }
 
+constexpr size_t HSTAGE_OUT = 2u << 20, HSTAGE_TOTAL = 8u << 20;
 __global__ void k_store_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
 // queue "copy `bytes` (multiple of 4) from device memory to offset `off` of the mapped staging buffer" on the
 // stream; the host reads c->hstage + off after synchronising the stream
-inline int stage_to_host(Ctx* c, size_t off, const void* d_src, size_t bytes) {
-    if (!c->hstage) {
-        const size_t cap = 8u << 20;
-        MS_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->hstage), cap, cudaHostAllocMapped));
-        MS_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hstage_dev), c->hstage, 0));
-        c->hstage_bytes = cap;
+inline int ensure_hstage(Ctx* c) {
+    if (c->hstage) return MS_OK;
+    MS_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->hstage), HSTAGE_TOTAL, cudaHostAllocMapped));
+    MS_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hstage_dev), c->hstage, 0));
+    c->hstage_bytes = HSTAGE_TOTAL;
+    return MS_OK;
+}
+// Small host -> device inputs (index lists, scan multipliers) the same way in the other direction: the host
+// writes them into the mapped buffer and a kernel copies them to `d_dst`, so they never wait on a copy engine
+// that is busy with bulk transfers.  Chunks are handed out by a bump allocator; when the region is full the
+// stream is drained first (everything queued so far has then consumed its chunk).
+inline int stage_from_host(Ctx* c, const void* h_src, size_t bytes, void* d_dst) {
+    MS_TRY(ensure_hstage(c));
+    if (bytes == 0) return MS_OK;
+    const size_t need = (bytes + 15) & ~(size_t)15, cap = c->hstage_bytes - HSTAGE_OUT;
+    if ((bytes & 3) || need > cap) return fail(c, MS_ERR_UNSUPPORTED, "staged input of %zu bytes", bytes);
+    if (c->hstage_in_used + need > cap) {
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->hstage_in_used = 0;
     }
-    if (off + bytes > c->hstage_bytes || (bytes & 3) || (off & 3)) return fail(c, MS_ERR_UNSUPPORTED, "staging buffer too small (%zu + %zu bytes)", off, bytes);
+    const size_t off = HSTAGE_OUT + c->hstage_in_used;
+    c->hstage_in_used += need;
+    memcpy(c->hstage + off, h_src, bytes);
+    const uint64_t n = bytes / 4;
+    k_store_words<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<uint32_t*>(d_dst),
+                                                                     reinterpret_cast<const uint32_t*>(c->hstage_dev + off), n);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+inline int stage_to_host(Ctx* c, size_t off, const void* d_src, size_t bytes) {
+    MS_TRY(ensure_hstage(c));
+    if (off + bytes > HSTAGE_OUT || (bytes & 3) || (off & 3)) return fail(c, MS_ERR_UNSUPPORTED, "staging buffer too small (%zu + %zu bytes)", off, bytes);
     const uint64_t n = bytes / 4;
     if (n == 0) return MS_OK;
     k_store_words<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->hstage_dev + off),

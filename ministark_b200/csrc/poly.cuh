@@ -375,7 +375,7 @@ int suffix_scan(Ctx* c, Src src, uint64_t len, uint32_t nbatch, const typename O
     }
     Scratch dmu(c);
     MS_TRY(dmu.alloc(hm.size() * sizeof(M)));
-    MS_CUDA(c, cudaMemcpyAsync(dmu.p, hm.data(), hm.size() * sizeof(M), cudaMemcpyHostToDevice, c->stream));
+    MS_TRY(stage_from_host(c, hm.data(), hm.size() * sizeof(M), dmu.p));  // not a copy-engine H2D: see common.cuh
     const M* d_mu = dmu.as<M>();
     const M* d_big = d_mu + nbatch;
     if (nblk == 1) {

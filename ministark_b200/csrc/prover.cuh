@@ -327,15 +327,22 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         // y1, y2 = prev.poly(x1), prev.poly(x2); y3 = round.poly(x3): evaluations at domain points are
         // codeword entries (exact arithmetic), so they are gathered instead of re-evaluated.
         Scratch d_idx(c), d_ys(c), d_found(c), d_neigh_idx(c), d_neigh(c), d_paths(c);
+        std::vector<E> ys(3 * QF);
+        const int path_len = ilog2(nd / 2);
+        std::vector<uint32_t> paths((size_t)2 * QF * path_len * 16);
+        std::vector<E> neigh(4 * QF);
+        // A rank that only contributes quotient polynomials to a shared proof buffer (pw.mute) needs none of the
+        // look-ups: they feed the fixed part, which rank 0 writes (sizes are data independent, so the offsets agree).
+        const bool lookups = !pw.mute;
+        if (lookups) {
         MS_TRY(d_idx.alloc(idx.size() * 8));
         MS_TRY(d_ys.alloc(3 * QF * sizeof(E)));
-        std::vector<E> ys(3 * QF);
         {
             // gather y1,y2 from prev.cw and y3 from nxt.cw: two launches over interleaved indices
             std::vector<unsigned long long> i12(2 * QF), i3(QF);
             for (uint64_t k = 0; k < QF; k++) { i12[2 * k] = idx[3 * k]; i12[2 * k + 1] = idx[3 * k + 1]; i3[k] = idx[3 * k + 2]; }
-            MS_CUDA(c, cudaMemcpyAsync(d_idx.p, i12.data(), i12.size() * 8, cudaMemcpyHostToDevice, c->stream));
-            MS_CUDA(c, cudaMemcpyAsync(d_idx.as<unsigned long long>() + 2 * QF, i3.data(), i3.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            MS_TRY(stage_from_host(c, i12.data(), i12.size() * 8, d_idx.p));
+            MS_TRY(stage_from_host(c, i3.data(), i3.size() * 8, d_idx.as<unsigned long long>() + 2 * QF));
             k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(prev.cw, prev.domain, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys.as<E>());
             MS_LAUNCH_CHECK(c);
             k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(nxt.cw, nxt.domain, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys.as<E>() + 2 * QF);
@@ -358,34 +365,43 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         for (auto f : found)
             if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
         q_host[0] += now_ms() - t_q; t_q = now_ms();
-        const int path_len = ilog2(nd / 2);
         std::vector<unsigned long long> nidx(4 * QF);
         for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = found[k] & ~1ULL; nidx[2 * k + 1] = found[k] | 1ULL; }
         MS_TRY(d_neigh_idx.alloc(nidx.size() * 8));
         MS_TRY(d_neigh.alloc(4 * QF * sizeof(E)));
         MS_TRY(d_paths.alloc((size_t)2 * QF * (path_len ? path_len : 1) * 64));
-        MS_CUDA(c, cudaMemcpyAsync(d_neigh_idx.p, nidx.data(), nidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        MS_TRY(stage_from_host(c, nidx.data(), nidx.size() * 8, d_neigh_idx.p));
         k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(prev.cw, prev.domain, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh.as<E>());
         MS_LAUNCH_CHECK(c);
-        std::vector<uint32_t> paths((size_t)2 * QF * path_len * 16);
         if (path_len) {
             int total = (int)(2 * QF) * path_len * 16;
             k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(prev.nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
             MS_LAUNCH_CHECK(c);
             MS_TRY(stage_to_host(c, 4 * QF * sizeof(E), d_paths.p, paths.size() * 4));
         }
-        std::vector<E> neigh(4 * QF);
         MS_TRY(stage_to_host(c, 0, d_neigh.p, 4 * QF * sizeof(E)));
-        // quotients (fri.rs:157-167)
+        }  // lookups
+        // quotients (fri.rs:157-167): only the ones this rank downloads (all of them unless the download is sharded)
         const uint64_t nq = prev.len >= 3 ? prev.len - 2 : 0;
         T* d_quot = nullptr;
+        std::vector<int> slot(QF, -1);  // query k's quotient is the slot[k]-th polynomial of d_quot
         if (nq) {
-            MS_TRY(dev_alloc((size_t)QF * nq * sizeof(E), (void**)&d_quot));
-            MS_TRY(fri_query_quotients<F>(c, prev.poly, prev.npad, prev.len, s2.data(), (uint32_t)QF, d_quot));
+            std::vector<T> s2_own;
+            for (uint64_t k = 0; k < QF; k++)
+                if ((copy_seq + k) % dl_world == dl_rank && !(hooks && hooks->replica_only && !dl_sharded)) {
+                    slot[k] = (int)s2_own.size();
+                    s2_own.push_back(s2[k]);
+                }
+            if (!s2_own.empty()) {
+                MS_TRY(dev_alloc(s2_own.size() * nq * sizeof(E), (void**)&d_quot));
+                MS_TRY(fri_query_quotients<F>(c, prev.poly, prev.npad, prev.len, s2_own.data(), (uint32_t)s2_own.size(), d_quot));
+            }
         }
         MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        memcpy(neigh.data(), c->hstage, 4 * QF * sizeof(E));
-        if (path_len) memcpy(paths.data(), c->hstage + 4 * QF * sizeof(E), paths.size() * 4);
+        if (lookups) {
+            memcpy(neigh.data(), c->hstage, 4 * QF * sizeof(E));
+            if (path_len) memcpy(paths.data(), c->hstage + 4 * QF * sizeof(E), paths.size() * 4);
+        }
         q_host[1] += now_ms() - t_q; t_q = now_ms();
         // ---- serialise this round (fri.rs:18-22, merkle.rs:293-298)
         pw.u64(QF);
@@ -410,14 +426,14 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             pw.u64(nq);
             if (nq) {
                 const uint64_t at = pw.reserve(nq * sizeof(E));
-                if (copy_seq++ % dl_world == dl_rank) copies.push_back({at, d_quot + (size_t)k * nq * D, (size_t)(nq * sizeof(E))});
+                if (slot[k] >= 0) copies.push_back({at, d_quot + (size_t)slot[k] * nq * D, (size_t)(nq * sizeof(E))});
             }
         }
+        if (nq) copy_seq += QF;
         q_host[2] += now_ms() - t_q; t_q = now_ms();
         // The quotient polynomials are ~all of the proof bytes (fri.rs:167): start this round's download on
         // the copy stream now, so it overlaps the next rounds' kernels and host work (the proof buffer was
         // checked against the size bound up front, so every offset is in range).
-        if (hooks && hooks->replica_only && !dl_sharded) copies.clear();
         if (!copies.empty()) {
             MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
             MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
