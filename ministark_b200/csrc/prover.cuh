@@ -283,6 +283,12 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     const bool dl_sharded = hooks && hooks->download_world > 1;
     const uint64_t dl_rank = dl_sharded ? (uint64_t)hooks->download_rank : 0, dl_world = dl_sharded ? (uint64_t)hooks->download_world : 1;
     uint64_t copy_seq = 0;
+    // Which rank downloads (and therefore computes) the seq-th quotient polynomial.  From 4 ranks on, rank 0 takes
+    // none: it is the only one that runs the look-ups and writes the fixed part, which is then the critical path.
+    auto owns = [&](uint64_t seq) -> bool {
+        if (dl_world >= 4) return dl_rank != 0 && seq % (dl_world - 1) + 1 == dl_rank;
+        return seq % dl_world == dl_rank;
+    };
     ProofWriter pw(proof_out, *proof_len);
     pw.mute = dl_sharded && dl_rank != 0;
     pw.bytes("MSTARKP1", 8);
@@ -388,7 +394,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         if (nq) {
             std::vector<T> s2_own;
             for (uint64_t k = 0; k < QF; k++)
-                if ((copy_seq + k) % dl_world == dl_rank && !(hooks && hooks->replica_only && !dl_sharded)) {
+                if (owns(copy_seq + k) && !(hooks && hooks->replica_only && !dl_sharded)) {
                     slot[k] = (int)s2_own.size();
                     s2_own.push_back(s2[k]);
                 }
