@@ -169,6 +169,76 @@ def test_sharded_commit_over_gloo_matches_oracle(world, k, oracle):
 
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
+class _NoCudaLib:
+    """ms_host_register / ms_host_unregister stand-ins: the shared-memory plumbing of SharedProofBuffer is host
+    code and is exercised here without a GPU (page-locking is the only CUDA call it makes)."""
+
+    def __init__(self):
+        self.registered = []
+
+    def ms_host_register(self, h, ptr, nbytes):
+        self.registered.append((ptr.value, nbytes))
+        return 0
+
+    def ms_host_unregister(self, h, ptr):
+        return 0
+
+
+class _NoCudaCtx:
+    h = None
+
+    def __init__(self):
+        self.lib = _NoCudaLib()
+
+    def _check(self, rc):
+        assert rc == 0
+
+
+def _shared_buffer_worker(rank, world, port, nbytes, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ministark_b200.sharded import SharedProofBuffer
+
+        ctx = _NoCudaCtx()
+        buf = SharedProofBuffer(ctx, nbytes, dist)
+        assert buf.array.size == nbytes and ctx.lib.registered == [(buf.array.ctypes.data, nbytes)]
+        # every rank writes the stripes a sharded download would give it (every world-th block of 1000 bytes)
+        for blk in range(rank, nbytes // 1000, world):
+            buf.array[blk * 1000:(blk + 1) * 1000] = (blk * 7 + 3) % 251
+        dist.barrier()
+        digest = hashlib.sha256(buf.array.tobytes()).hexdigest()  # every rank sees every rank's bytes
+        buf.close()
+        q.put((rank, digest))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_proof_buffer_over_gloo(world):
+    """One POSIX shared-memory proof buffer per node: created by rank 0, attached (and page-locked) by the others,
+    written in disjoint stripes by all ranks, identical from every rank's point of view, unlinked at close."""
+    import torch.multiprocessing as mp
+
+    nbytes = 64 * 1000
+    want = np.zeros(nbytes, dtype=np.uint8)
+    for blk in range(nbytes // 1000):
+        want[blk * 1000:(blk + 1) * 1000] = (blk * 7 + 3) % 251
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_shared_buffer_worker, args=(r, world, port, nbytes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(d == hashlib.sha256(want.tobytes()).hexdigest() for _, d in got)
+
+
 @pytest.mark.parametrize("field", [0, 1])
 @pytest.mark.parametrize("log_n,w,blowup,k", [(8, 4, 8, 2), (10, 8, 4, 8), (11, 4, 8, 4)])
 def test_hooked_prover_world1_equals_plain(field, log_n, w, blowup, k):
