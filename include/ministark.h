@@ -183,16 +183,18 @@ typedef struct ms_commit_hooks {
     int32_t (*trace_commit)(void* user, const void* d_trace_colmajor, uint64_t n, uint64_t w, uint8_t* root32);
     int32_t (*lde_commit)(void* user, const void* d_coeffs_colmajor, uint64_t n, uint64_t cols, uint64_t blowup,
                           uint64_t shift, uint8_t* root32);
-    /* non-zero on ranks whose proof bytes nobody reads (every rank but one): all stages still run, so the
-     * transcript and the device state stay in lock step, but the per-query quotient polynomials -- ~all of
-     * the proof bytes, src/fri.rs:167 -- are not downloaded (N simultaneous multi-GB PCIe reads would
-     * only slow rank 0 down).  proof_out then holds the fixed part and *proof_len the full length. */
+    /* non-zero on ranks whose proof bytes nobody reads (every rank but one): every stage that feeds the
+     * transcript still runs, so all ranks stay in lock step, but the per-query quotient polynomials -- ~all
+     * of the proof bytes, src/fri.rs:167 -- are neither computed nor downloaded (N simultaneous multi-GB
+     * PCIe reads would only slow rank 0 down).  proof_out then holds the fixed part and *proof_len the full
+     * length. */
     int32_t replica_only;
     /* Sharded proof download (download_world > 1): proof_out is then ONE host buffer shared by all ranks
      * (e.g. POSIX shared memory, page-locked in every process with ms_host_register).  Every replica holds the
-     * same quotient polynomials, so rank r downloads only every download_world-th of them (r, r + world, ...)
-     * over its own PCIe link, each to its final offset; rank 0 also writes the fixed part.  The caller adds a
-     * barrier after the call.  replica_only is ignored in this mode. */
+     * codewords, so each rank computes and downloads only its share of the quotient polynomials over its own
+     * PCIe link, each to its final offset (round robin over all ranks; from 4 ranks on over ranks 1..world-1,
+     * because rank 0 alone runs the look-ups and writes the fixed part).  The caller adds a barrier after the
+     * call.  replica_only is ignored in this mode. */
     int32_t download_rank;
     int32_t download_world;
 } ms_commit_hooks;
