@@ -200,8 +200,54 @@ static int check(int logN, int logB, bool inverse, int force_a, uint64_t cols) {
     return bad;
 }
 
+// The register block on its own: gl_shift_dft<G, INV> (power-of-two twiddles, lazy inputs in every slot but the
+// stage-0 operands) against the defining sum over ark's root of unity, and x * 2^S against repeated doubling.
+template <int G, bool INV>
+static int check_shift_block(uint64_t seed) {
+    constexpr int E = 1 << G;
+    uint64_t v[E], in[E];
+    uint64_t s = seed;
+    for (int r = 0; r < E; r++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        // odd slots are stage-0 operands (canonical by contract); even slots may be any 64-bit representative
+        in[r] = (r & 1) ? s % GL::P : (r % 4 == 0 ? s | 0xFFFFFFFF00000000ULL : s);
+        v[r] = in[r];
+    }
+    gl_shift_dft<G, INV>(v);
+    uint64_t w = root_of_unity<GL>(G);
+    if (INV) w = finv<GL>(w);
+    int bad = 0;
+    for (int k = 0; k < E; k++) {
+        uint64_t acc = 0;
+        for (int r = 0; r < E; r++)  // DIT: slot r holds sub-index brev(r)
+            acc = GL::add(acc, GL::mul(in[r] % GL::P, fpow<GL>(w, (uint64_t)cbrev(r, G) * k)));
+        if (v[k] % GL::P != acc) bad++;
+    }
+    printf("shift block G=%d inv=%d: %s\n", G, (int)INV, bad ? "MISMATCH" : "ok");
+    return bad;
+}
+template <int S>
+static int check_mulpow2_from() {
+    if constexpr (S < 96) {
+        int bad = 0;
+        const uint64_t xs[] = {0, 1, GL::P - 1, GL::P, ~0ULL, 0xFFFFFFFFULL, 0x100000000ULL, 0x123456789ABCDEF1ULL, 0xFFFFFFFF00000001ULL};
+        for (uint64_t x : xs) {
+            uint64_t want = x % GL::P;
+            for (int d = 0; d < S; d++) want = GL::add(want, want);
+            if (Fast<GL>::mulpow2<S>(x) != want) bad++;
+        }
+        if (bad) printf("mulpow2<%d>: MISMATCH\n", S);
+        return bad + check_mulpow2_from<S + 1>();
+    } else {
+        return 0;
+    }
+}
+
 int main() {
     int bad = 0;
+    bad += check_shift_block<1, false>(11) + check_shift_block<2, false>(12) + check_shift_block<3, false>(13) + check_shift_block<4, false>(14);
+    bad += check_shift_block<1, true>(21) + check_shift_block<2, true>(22) + check_shift_block<3, true>(23) + check_shift_block<4, true>(24);
+    bad += check_mulpow2_from<1>();
     for (int logN = 0; logN <= 11; logN++)
         for (int logB = 0; logB <= 3; logB++) {
             bad += check<GL>(logN, logB, false, -1, 2);
