@@ -2,7 +2,8 @@
 the compile-time-shaped k_ntt_fixed) are __host__ __device__, so tests/emul/emul_ntt.cu runs them thread by
 thread on the host -- tile geometry, round split, shared-memory swizzle, bit-reversed gathers, two-pass
 index maps (in place and through a temporary), coset-folded twiddles and the inter-pass factor table --
-against a naive Horner evaluation, for both fields.  (The PTX arithmetic itself is covered on the GPU by
+against a naive Horner evaluation, for both fields; the Goldilocks register block with power-of-two twiddles
+(gl_shift_dft, both directions) and x * 2^S for every S in 1..95 are also checked on their own.  (The PTX arithmetic itself is covered on the GPU by
 test_butterfly_arithmetic_selftest.)"""
 import os
 import shutil
