@@ -81,8 +81,9 @@ class StarkProof:  # starks.rs:21-28
 
 class StarkConfig:
     """StarkConfig::new(security_bits, blowup_factor, steps, trace_columns) (starks.rs:268-310).
-    `inner_children` is an extension: the reference hard-wires 2 (starks.rs:299); BASELINE configs 3 and
-    5 use 4-/8-ary trees, which merkle.rs supports."""
+    `inner_children` is an extension: the reference hard-wires 2 (starks.rs:283-302).  merkle.rs supports
+    k-ary trees but only full ones (merkle.rs:93-104): BASELINE configs 3 and 5 as written (2^23 rows 4-ary,
+    2^26 rows 8-ary) are rejected with its "Tree is not full!" (DESIGN.md section 8)."""
 
     def __init__(self, field: StarkField, security_bits: int, blowup_factor: int, steps: int, trace_columns: int,
                  inner_children: int = 2):

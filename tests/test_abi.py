@@ -102,6 +102,39 @@ def test_trace_table_mirror_matches_air_rs(pyref):
     assert t.constrain_number() == 5
 
 
+@pytest.mark.parametrize("name,steps", [("Goldilocks", 9), ("BabyBear", 7)])
+def test_proof_dump_parser_round_trips_the_oracle_proofs(name, steps, pyref):
+    """StarkProof.from_bytes (the host mirror's parser of the canonical dump) against the
+    restated reference prover on the two reference e2e configurations (tests/e2e_goldilocks.rs,
+    tests/e2e_babybear.rs): same bytes as the committed golden hashes, every field recovered."""
+    import hashlib
+    import json
+
+    from ministark_b200.starks import StarkProof
+
+    F = getattr(pyref, name)
+    claim = pyref.FibonacciClaim(F, steps)
+    trace = claim.trace(2)
+    cfg = pyref.StarkConfig(F, 20, 2, trace.step_number(), trace.constrain_number())
+    ref = pyref.Stark(cfg).prove(claim, 2)
+    raw = pyref.serialize_proof(F, ref)
+    with open(os.path.join(ROOT, "tests", "golden", "e2e_proofs.json")) as fh:
+        golden = json.load(fh)[name]
+    assert len(raw) == golden["proof_len"] and hashlib.sha256(raw).hexdigest() == golden["proof_sha256"]
+    got = StarkProof.from_bytes(raw)
+    assert got.arthur == ref.arthur and got.trace_commit == ref.trace_commit
+    assert got.trace_commit.hex() == golden["trace_commit"]
+    assert got.constrain_trace_commit == ref.constrain_trace_commit
+    norm = lambda e: tuple(int(c) for c in (e if isinstance(e, (tuple, list)) else (e,)))
+    assert [[norm(e) for e in row] for row in got.constrain_queries] == [[norm(e) for e in row] for row in ref.constrain_queries]
+    assert [norm(e) for e in got.validity_queries] == [norm(e) for e in ref.validity_queries]
+    assert len(got.fri_proof.points) == len(ref.fri_proof.points) == golden["rounds"] - 1
+    assert all(len(r) == golden["fri_queries"] for r in got.fri_proof.quotients)
+    for gr, rr in zip(got.fri_proof.quotients, ref.fri_proof.quotients):
+        for gq, rq in zip(gr, rr):
+            assert [norm(e) for e in gq] == [norm(e) for e in rq]
+
+
 def test_product_does_not_touch_the_oracle():
     pkg = os.path.join(ROOT, "ministark_b200")
     for dirpath, _dirs, files in os.walk(pkg):
