@@ -168,7 +168,6 @@ def test_sharded_commit_over_gloo_matches_oracle(world, k, oracle):
 
 
 # ------------------------------------------------------------------------------------------ GPU
-@pytest.mark.gpu
 class _NoCudaLib:
     """ms_host_register / ms_host_unregister stand-ins: the shared-memory plumbing of SharedProofBuffer is host
     code and is exercised here without a GPU (page-locking is the only CUDA call it makes)."""
@@ -239,6 +238,7 @@ def test_shared_proof_buffer_over_gloo(world):
     assert all(d == hashlib.sha256(want.tobytes()).hexdigest() for _, d in got)
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("field", [0, 1])
 @pytest.mark.parametrize("log_n,w,blowup,k", [(8, 4, 8, 2), (10, 8, 4, 8), (11, 4, 8, 4)])
 def test_hooked_prover_world1_equals_plain(field, log_n, w, blowup, k):
