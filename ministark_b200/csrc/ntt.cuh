@@ -10,8 +10,8 @@
 // of the zero padded size-L transform are pure replication and are never executed).
 //
 // Work decomposition.  N = n1 * n2 (n2 = 2^a, n1 = 2^b) is covered by at most two passes over
-// HBM; both passes run the same kernel, k_ntt_tile, on a "tile" = [2^a' points] x [2^beta batch
-// entries] that lives in shared memory (8192 or 16384 elements):
+// HBM; both passes run the same kernel (k_ntt_fixed for the planner's shapes, k_ntt_tile otherwise) on a
+// "tile" = [2^a' points] x [2^beta batch entries] of 8192 elements that lives in shared memory:
 //
 //   pass 1  transform along m2 (stride n1 in the input) for R consecutive m1 and all B cosets.
 //           The coset shift is folded into the stage twiddles t1[j][2^s+q] = s_j^(N/2^(s+1)) w_(2^(s+1))^q
@@ -31,7 +31,10 @@
 // Arithmetic (Goldilocks): butterflies run on lazily reduced values.  mul() returns a canonical
 // product, add()/sub() take (lazy, canonical) and return lazy values in [0, 2^64); carries are
 // folded back with 2^64 = 2^32 - 1 (mod p) through PTX carry chains (see Fast<GL>).  Everything
-// written to HBM is canonical.  BabyBear keeps canonical data and Montgomery-form twiddles.
+// written to HBM is canonical.  In the fixed-shape kernel a Goldilocks round is "multiply element r
+// by beta^brev(r), then a plain DFT-2^G whose twiddles are powers of two" (ShiftTw, gl_shift_dft,
+// tw16_entry): one general product per element per round, shifts inside.  BabyBear keeps canonical
+// data, Montgomery-form twiddles and radix-2 butterflies; so does the generic k_ntt_tile.
 #pragma once
 #include "common.cuh"
 #include "field.cuh"
@@ -39,8 +42,7 @@
 namespace ms {
 
 constexpr int NTT_MAXLOG = 14;         // largest in-tile transform (plain twiddle table size)
-constexpr int NTT_LOG_TILE_PREF = 13;  // preferred tile: 8192 elements (64 KB Goldilocks, 2 CTAs / SM)
-constexpr int NTT_LOG_TILE_MAX = 14;   // 128 KB Goldilocks tile, one CTA per SM
+constexpr int NTT_LOG_TILE_PREF = 13;  // tile: 8192 elements (64 KB Goldilocks, 3 CTAs / SM)
 constexpr int NTT_THREADS = 256;
 constexpr int NTT_MAXG = 4;            // stages per round: 16 elements in registers
 #ifndef MS_NTT_MINB
