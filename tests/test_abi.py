@@ -135,6 +135,15 @@ def test_proof_dump_parser_round_trips_the_oracle_proofs(name, steps, pyref):
             assert [norm(e) for e in gq] == [norm(e) for e in rq]
 
 
+def test_integration_doc_binds_every_declared_symbol():
+    """INTEGRATION.md's Rust `extern "C"` block (what a maintainer of the reference adds) names every entry point
+    include/ministark.h declares."""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as fh:
+        doc = fh.read()
+    missing = [name for name in _declared_symbols() if f"fn {name}(" not in doc]
+    assert not missing, missing
+
+
 def test_product_does_not_touch_the_oracle():
     pkg = os.path.join(ROOT, "ministark_b200")
     for dirpath, _dirs, files in os.walk(pkg):
