@@ -64,6 +64,13 @@ int32_t ms_set_profiling(ms_ctx* ctx, int32_t on);
 int32_t ms_profile_collect(ms_ctx* ctx, const char** names, float* total_ms, uint32_t* counts, int32_t cap);
 /* Display of the zero element: 0 -> "0" (ark-ff 0.5.0, default), 1 -> "" (ark-ff 0.4.x) */
 int32_t ms_set_zero_display(ms_ctx* ctx, int32_t empty);
+/* Switches of the host transcript's nimue restatement (third-party crate, not in the reference tree; csrc/transcript.hpp):
+ * MS_OPT_MASK_ABSORB / _SQUEEZE / _SQUEEZE_END = first byte of DigestBridge's three domain-separation blocks (0, 1, 2);
+ * MS_OPT_LEFTOVER_AS_PUBLISHED = 1 (default): squeeze consumes digest bytes left over from the previous squeeze call
+ * without writing them to the output, as nimue@0e584985's leftovers branch does; 0: the intended behaviour.
+ * Replaces: nothing in the reference tree -- nimue call sites src/starks.rs:81,108,125, src/fri.rs:89,96,122. */
+enum { MS_OPT_MASK_ABSORB = 0, MS_OPT_MASK_SQUEEZE = 1, MS_OPT_MASK_SQUEEZE_END = 2, MS_OPT_LEFTOVER_AS_PUBLISHED = 3 };
+int32_t ms_set_transcript_option(ms_ctx* ctx, int32_t option, int32_t value);
 
 /* Device self-test of the lazy / Montgomery butterfly arithmetic (csrc/ntt.cuh Fast<F>) against exact host
  * arithmetic on edge values and n_random random operand pairs; *n_bad = mismatches (0 expected). */
@@ -143,6 +150,19 @@ int32_t ms_fri_deep_coeffs(ms_ctx* ctx, const void* d_poly, uint64_t stride, uin
  * Replaces: src/fri.rs:97-101 with fold_poly :361-372. */
 int32_t ms_fri_fold(ms_ctx* ctx, const void* d_poly, uint64_t stride, uint64_t n_coeffs, const void* z_host,
                     const void* alpha_host, const void* d_host, void* d_next, uint64_t next_stride);
+
+/* One round of the query phase for q betas (usize values as squeezed, src/fri.rs:121-126): prev / next are two consecutive
+ * committed rounds (codewords as D planes, prev's (2,2) tree nodes from ms_fri_commit, prev's polynomial with prev_len
+ * coefficients).  Host outputs: points [q][6][D] = x1,y1,x2,y2,x3,y3 (src/fri.rs:148-154); found [2q] = leaf index the value
+ * search returns for y1, y2 (first match, src/merkle.rs:216-225); neigh [2q][2][D] leaf neighbours; paths
+ * [2q][log2(prev_domain/2)][2][32] sibling pairs, digest bytes (src/merkle.rs:238-265); quot [q][prev_len-2][D] quotient
+ * coefficients (src/fri.rs:157-167; nothing written when prev_len < 3).  Any output pointer may be NULL.
+ * Replaces: the body of the round loop of Fri::query_phase, src/fri.rs:132-176, with MerkleTree::generate_proof,
+ * src/merkle.rs:272-288. */
+int32_t ms_fri_query(ms_ctx* ctx, const void* d_prev_poly, uint64_t poly_stride, uint64_t prev_len, const void* d_prev_cw,
+                     uint64_t prev_cw_stride, uint64_t prev_domain, const uint32_t* d_prev_nodes, const void* d_next_cw,
+                     uint64_t next_cw_stride, const uint64_t* betas_host, uint64_t q, void* points_host, uint64_t* found_host,
+                     void* neigh_host, uint8_t* paths_host, void* quot_host);
 
 /* ---- whole prover ------------------------------------------------------------------------------------ */
 typedef struct ms_stark_params {

@@ -45,6 +45,7 @@ SIGNATURES = {
     "ms_sync": (_i32, [_vp]),
     "ms_launch_count": (_u64, [_vp]),
     "ms_set_zero_display": (_i32, [_vp, _i32]),
+    "ms_set_transcript_option": (_i32, [_vp, _i32, _i32]),
     "ms_set_profiling": (_i32, [_vp, _i32]),
     "ms_profile_collect": (_i32, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), _i32]),
     "ms_selftest_field_ops": (_i32, [_vp, _u64, C.POINTER(_u64)]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "ms_fri_commit": (_i32, [_vp, _vp, _u64, _u64, _u64, _vp, _u64, _vp, _vp]),
     "ms_fri_deep_coeffs": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "ms_fri_fold": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64]),
+    "ms_fri_query": (_i32, [_vp, _vp, _u64, _u64, _vp, _u64, _u64, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "ms_stark_derive": (_i32, [_i32, C.POINTER(StarkParams), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "ms_stark_proof_bound": (_u64, [_i32, C.POINTER(StarkParams), _u64, _u64]),
     "ms_stark_prove": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),

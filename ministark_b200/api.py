@@ -84,6 +84,10 @@ class Context:
     def set_zero_display(self, empty: bool):
         self._check(self.lib.ms_set_zero_display(self.h, int(empty)))
 
+    def set_transcript_option(self, option: int, value: int):
+        """ms_set_transcript_option: 0-2 DigestBridge mask bytes, 3 leftover handling as published (1) / intended (0)"""
+        self._check(self.lib.ms_set_transcript_option(self.h, option, value))
+
     def to_device(self, a: np.ndarray):
         torch = _torch()
         a = np.ascontiguousarray(a, dtype=self.np_dtype)
@@ -216,6 +220,25 @@ class Context:
         self._check(self.lib.ms_fri_fold(self.h, self._ptr(poly_planes), poly_planes.stride(0), n, zz.ctypes.data, aa.ctypes.data,
                                          dd.ctypes.data, self._ptr(out), out.stride(0)))
         return out
+
+    def fri_query(self, prev_poly, prev_len: int, prev_cw, prev_nodes, next_cw, betas: Sequence[int], want_quot: bool = True):
+        """One round of the query phase (fri.rs:132-176).  Returns dict(points [q,6,D], found [2q], neigh [2q,2,D],
+        paths [2q, path_len, 2, 32] bytes, quot [q, prev_len-2, D])."""
+        D, nd = prev_cw.shape
+        q = len(betas)
+        b = np.ascontiguousarray(betas, dtype=np.uint64)
+        path_len = max((nd // 2).bit_length() - 1, 0)
+        pts = np.zeros((q, 6, D), dtype=self.np_dtype)
+        found = np.zeros(2 * q, dtype=np.uint64)
+        neigh = np.zeros((2 * q, 2, D), dtype=self.np_dtype)
+        paths = np.zeros((2 * q, path_len, 2, 32), dtype=np.uint8)
+        nq = max(prev_len - 2, 0)
+        quot = np.zeros((q, nq, D), dtype=self.np_dtype) if want_quot else None
+        self._check(self.lib.ms_fri_query(self.h, self._ptr(prev_poly), prev_poly.stride(0), prev_len, self._ptr(prev_cw), prev_cw.stride(0),
+                                          nd, self._ptr(prev_nodes), self._ptr(next_cw), next_cw.stride(0), b.ctypes.data, q,
+                                          pts.ctypes.data, found.ctypes.data, neigh.ctypes.data, paths.ctypes.data,
+                                          quot.ctypes.data if quot is not None and nq else None))
+        return dict(points=pts, found=found, neigh=neigh, paths=paths, quot=quot)
 
     # ---------------------------------------------------------------- whole prover
     def stark_prove(self, params: StarkParams, trace_rm: np.ndarray, constraint_matrix: np.ndarray,

@@ -37,6 +37,7 @@ struct Ctx {
     std::vector<ProfEntry> prof;
     // transcript switches (host prover)
     uint8_t bridge_masks[3] = {0x00, 0x01, 0x02};
+    int leftover_as_published = 1;  // nimue DigestBridge leftovers branch as published (see transcript.hpp)
 };
 
 inline int fail(Ctx* c, int code, const char* fmt, ...) {

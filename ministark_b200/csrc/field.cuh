@@ -70,7 +70,7 @@ struct GL {
 struct BB {
     using T = uint32_t;
     static constexpr int ID = 1;
-    static constexpr int D = 4;  // Fp4 = Fp2[v]/(v^2 - (u - 11)), Fp2 = Fp[u]/(u^2 - 11)
+    static constexpr int D = 4;  // Fp4 = Fp2[v]/(v^2 - u) (ark-ff's effective tower, see ext_mul), Fp2 = Fp[u]/(u^2 - 11)
     static constexpr T P = 2013265921u;
     static constexpr T ROOT = 291241980u;
     static constexpr int TWO_ADICITY = 27;
@@ -181,18 +181,22 @@ MS_HD Ext<GL> ext_mul(const Ext<GL>& a, const Ext<GL>& b) {
     fp2_mul<GL>(a.c, b.c, r.c);
     return r;
 }
+// BabyBearFp4 (field.rs:93-109).  The tower ark-ff 0.5.0 actually computes in is v^2 = u: QuadExtField's
+// mul/square/inverse call Fp4Config::mul_fp2_by_nonresidue_in_place, whose default body is
+// (c0, c1) -> (Fp2::NONRESIDUE * c1, c0), i.e. multiplication by u, and the reference does not override it
+// (the trait doc says NONRESIDUE "must equal (0, 1)").  The declared constant (2013265910, 1) = u - 11 of
+// field.rs:96 is never read on the prover path; the declared Frobenius coefficients 11^((q^i-1)/4)
+// (field.rs:98-107) are those of v^4 = 11, i.e. of v^2 = u.  [ark-ff source is not in this image: recalled.]
 MS_HD Ext<BB> ext_mul(const Ext<BB>& a, const Ext<BB>& b) {
     using T = BB::T;
-    const T xi[2] = {BB::P - 11, 1};  // v^2 = u - 11 (field.rs:96)
-    T a0b0[2], a1b1[2], a0b1[2], a1b0[2], t[2];
+    T a0b0[2], a1b1[2], a0b1[2], a1b0[2];
     fp2_mul<BB>(&a.c[0], &b.c[0], a0b0);
     fp2_mul<BB>(&a.c[2], &b.c[2], a1b1);
     fp2_mul<BB>(&a.c[0], &b.c[2], a0b1);
     fp2_mul<BB>(&a.c[2], &b.c[0], a1b0);
-    fp2_mul<BB>(a1b1, xi, t);
     Ext<BB> r;
-    r.c[0] = BB::add(a0b0[0], t[0]);
-    r.c[1] = BB::add(a0b0[1], t[1]);
+    r.c[0] = BB::add(a0b0[0], BB::mul_small(a1b1[1], (uint32_t)BB::NONRES));  // u * (x + y u) = 11 y + x u
+    r.c[1] = BB::add(a0b0[1], a1b1[0]);
     r.c[2] = BB::add(a0b1[0], a1b0[0]);
     r.c[3] = BB::add(a0b1[1], a1b0[1]);
     return r;

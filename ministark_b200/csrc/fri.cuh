@@ -175,4 +175,89 @@ __global__ void k_gather_paths(const uint32_t* __restrict__ nodes, uint64_t n_gr
     out[tid] = nodes[(off + pair) * 8 + w];
 }
 
+// One round of Fri::query_phase (src/fri.rs:132-176) for the betas of the transcript: the three points per query
+// (y1, y2 = prev.poly at x1 = g^beta, x2 = -x1; y3 = next.poly at x3 = x1^2: evaluations at domain points are codeword
+// entries, so they are gathered, not re-evaluated), and the two Merkle openings by value search (first leaf equal to y,
+// src/merkle.rs:216-225) with leaf neighbours and sibling pairs (src/merkle.rs:230-265).  Results arrive in host memory
+// through the mapped staging buffer; the stream is synchronised once per step (look-ups, then neighbours + paths).
+template <class F>
+struct QueryLookups {
+    std::vector<typename F::T> x1, x2, x3, s2;     // [q] domain points, s2 = x1^2
+    std::vector<Ext<F>> ys;                          // [3q]: y1,y2 interleaved per query (2k, 2k+1), then the q y3's
+    std::vector<unsigned long long> found;           // [2q] leaf index of y1, y2
+    std::vector<Ext<F>> neigh;                       // [4q] the two leaves of each found leaf's group
+    std::vector<uint32_t> paths;                     // [2q][path_len][2][8] digest words
+    int path_len = 0;
+};
+template <class F>
+int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stride, uint64_t nd, const uint32_t* d_prev_nodes,
+                      const typename F::T* d_next_cw, uint64_t next_stride, uint64_t next_domain, const uint64_t* betas, uint64_t QF,
+                      QueryLookups<F>* out) {
+    using T = typename F::T;
+    using E = Ext<F>;
+    if (!is_pow2(nd) || nd < 2 || next_domain * 2 != nd) return fail(c, MS_ERR_BAD_SHAPE, "FRI query: domains %llu -> %llu", (unsigned long long)nd, (unsigned long long)next_domain);
+    const T g_prev = root_of_unity<F>(ilog2(nd)), g_next = root_of_unity<F>(ilog2(next_domain));
+    std::vector<unsigned long long> i12(2 * QF), i3(QF);
+    out->x1.resize(QF); out->x2.resize(QF); out->x3.resize(QF); out->s2.resize(QF);
+    for (uint64_t k = 0; k < QF; k++) {
+        uint64_t beta = betas[k];
+        if (beta > nd) beta %= nd;                                                   // fri.rs:144 (strict >)
+        out->x1[k] = fpow<F>(g_prev, beta);                                          // fri.rs:148
+        out->x2[k] = fpow<F>(g_prev, next_domain + beta);                            // fri.rs:149
+        out->x3[k] = fpow<F>(g_next, beta);                                          // fri.rs:150
+        out->s2[k] = F::mul(out->x1[k], out->x1[k]);
+        i12[2 * k] = beta % nd;
+        i12[2 * k + 1] = (next_domain + beta) % nd;
+        i3[k] = beta % next_domain;
+    }
+    const int path_len = ilog2(nd / 2);
+    out->path_len = path_len;
+    out->ys.resize(3 * QF); out->found.resize(2 * QF); out->neigh.resize(4 * QF);
+    out->paths.assign((size_t)2 * QF * path_len * 16, 0);
+    Scratch d_idx(c), d_ys(c), d_found(c), d_neigh_idx(c), d_neigh(c), d_paths(c);
+    MS_TRY(d_idx.alloc(3 * QF * 8));
+    MS_TRY(d_ys.alloc(3 * QF * sizeof(E)));
+    MS_TRY(stage_from_host(c, i12.data(), i12.size() * 8, d_idx.p));
+    MS_TRY(stage_from_host(c, i3.data(), i3.size() * 8, d_idx.as<unsigned long long>() + 2 * QF));
+    k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys.as<E>());
+    MS_LAUNCH_CHECK(c);
+    k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(d_next_cw, next_stride, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys.as<E>() + 2 * QF);
+    MS_LAUNCH_CHECK(c);
+    MS_TRY(d_found.alloc(2 * QF * 8));
+    MS_CUDA(c, cudaMemsetAsync(d_found.p, 0xff, 2 * QF * 8, c->stream));
+    k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(d_prev_cw, prev_stride, nd, d_ys.as<E>(), (int)(2 * QF), d_found.as<unsigned long long>());
+    MS_LAUNCH_CHECK(c);
+    // small results go through mapped pinned memory, not the copy engine: a D2H copy here would queue behind the
+    // previous rounds' multi-MB quotient downloads and serialise the query loop with the download
+    const size_t ys_bytes = 3 * QF * sizeof(E), found_bytes = 2 * QF * 8;
+    MS_TRY(stage_to_host(c, 0, d_ys.p, ys_bytes));
+    MS_TRY(stage_to_host(c, ys_bytes, d_found.p, found_bytes));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(out->ys.data(), c->hstage, ys_bytes);
+    memcpy(out->found.data(), c->hstage + ys_bytes, found_bytes);
+    for (auto f : out->found)
+        if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
+    std::vector<unsigned long long> nidx(4 * QF);
+    for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = out->found[k] & ~1ULL; nidx[2 * k + 1] = out->found[k] | 1ULL; }
+    MS_TRY(d_neigh_idx.alloc(nidx.size() * 8));
+    MS_TRY(d_neigh.alloc(4 * QF * sizeof(E)));
+    MS_TRY(d_paths.alloc((size_t)2 * QF * (path_len ? path_len : 1) * 64));
+    MS_TRY(stage_from_host(c, nidx.data(), nidx.size() * 8, d_neigh_idx.p));
+    k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh.as<E>());
+    MS_LAUNCH_CHECK(c);
+    if (path_len) {
+        int total = (int)(2 * QF) * path_len * 16;
+        k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
+        MS_LAUNCH_CHECK(c);
+        MS_TRY(stage_to_host(c, 4 * QF * sizeof(E), d_paths.p, out->paths.size() * 4));
+    }
+    MS_TRY(stage_to_host(c, 0, d_neigh.p, 4 * QF * sizeof(E)));
+    return MS_OK;  // the caller synchronises the stream, then calls fri_query_lookups_finish
+}
+template <class F>
+void fri_query_lookups_finish(Ctx* c, uint64_t QF, QueryLookups<F>* out) {
+    memcpy(out->neigh.data(), c->hstage, 4 * QF * sizeof(Ext<F>));
+    if (out->path_len) memcpy(out->paths.data(), c->hstage + 4 * QF * sizeof(Ext<F>), out->paths.size() * 4);
+}
+
 }  // namespace ms

@@ -81,6 +81,42 @@ static int coset_lde_host(Ctx* c, const void* coeffs_host, uint64_t n, uint64_t 
     return MS_OK;
 }
 
+template <class F>
+static int fri_query_export(Ctx* c, const void* d_prev_poly, uint64_t poly_stride, uint64_t prev_len, const void* d_prev_cw,
+                            uint64_t prev_cw_stride, uint64_t prev_domain, const uint32_t* d_prev_nodes, const void* d_next_cw,
+                            uint64_t next_cw_stride, const uint64_t* betas, uint64_t q, void* points_host, uint64_t* found_host,
+                            void* neigh_host, uint8_t* paths_host, void* quot_host) {
+    using T = typename F::T;
+    using E = Ext<F>;
+    if (q == 0) return MS_OK;
+    QueryLookups<F> lk;
+    MS_TRY(fri_query_lookups<F>(c, (const T*)d_prev_cw, prev_cw_stride, prev_domain, d_prev_nodes, (const T*)d_next_cw, next_cw_stride,
+                                prev_domain / 2, betas, q, &lk));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    fri_query_lookups_finish<F>(c, q, &lk);
+    if (points_host) {
+        E* pts = reinterpret_cast<E*>(points_host);
+        for (uint64_t k = 0; k < q; k++) {
+            pts[6 * k + 0] = ext_from_base<F>(lk.x1[k]); pts[6 * k + 1] = lk.ys[2 * k];
+            pts[6 * k + 2] = ext_from_base<F>(lk.x2[k]); pts[6 * k + 3] = lk.ys[2 * k + 1];
+            pts[6 * k + 4] = ext_from_base<F>(lk.x3[k]); pts[6 * k + 5] = lk.ys[2 * q + k];
+        }
+    }
+    if (found_host) for (uint64_t k = 0; k < 2 * q; k++) found_host[k] = lk.found[k];
+    if (neigh_host) memcpy(neigh_host, lk.neigh.data(), 4 * q * sizeof(E));
+    if (paths_host)
+        for (size_t i = 0; i < lk.paths.size() / 8; i++) digest_words_to_bytes(&lk.paths[8 * i], paths_host + 32 * i);
+    if (quot_host && prev_len >= 3) {
+        const uint64_t nq = prev_len - 2;
+        Scratch dq(c);
+        MS_TRY(dq.alloc(q * nq * sizeof(E)));
+        MS_TRY(fri_query_quotients<F>(c, (const T*)d_prev_poly, poly_stride, prev_len, lk.s2.data(), (uint32_t)q, dq.as<T>()));
+        MS_CUDA(c, cudaMemcpyAsync(quot_host, dq.p, q * nq * sizeof(E), cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return MS_OK;
+}
+
 extern "C" {
 
 int32_t ms_version(void) { return 1; }
@@ -165,6 +201,13 @@ int32_t ms_profile_collect(ms_ctx* c, const char** names, float* total_ms, uint3
 }
 int32_t ms_set_zero_display(ms_ctx* c, int32_t empty) {
     c->zero_display_empty = empty ? 1 : 0;
+    return MS_OK;
+}
+
+int32_t ms_set_transcript_option(ms_ctx* c, int32_t option, int32_t value) {
+    if (option >= MS_OPT_MASK_ABSORB && option <= MS_OPT_MASK_SQUEEZE_END) c->bridge_masks[option] = (uint8_t)value;
+    else if (option == MS_OPT_LEFTOVER_AS_PUBLISHED) c->leftover_as_published = value ? 1 : 0;
+    else return fail(c, MS_ERR_UNSUPPORTED, "unknown transcript option %d", option);
     return MS_OK;
 }
 
@@ -278,6 +321,15 @@ int32_t ms_fri_deep_coeffs(ms_ctx* c, const void* d_poly, uint64_t stride, uint6
 int32_t ms_fri_fold(ms_ctx* c, const void* d_poly, uint64_t stride, uint64_t n_coeffs, const void* z_host, const void* alpha_host,
                     const void* d_host, void* d_next, uint64_t next_stride) {
 #define CALL(F) fri_fold<F>(c, (const F::T*)d_poly, stride, n_coeffs, (const F::T*)z_host, (const F::T*)alpha_host, (const F::T*)d_host, (F::T*)d_next, next_stride)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_fri_query(ms_ctx* c, const void* d_prev_poly, uint64_t poly_stride, uint64_t prev_len, const void* d_prev_cw,
+                     uint64_t prev_cw_stride, uint64_t prev_domain, const uint32_t* d_prev_nodes, const void* d_next_cw,
+                     uint64_t next_cw_stride, const uint64_t* betas_host, uint64_t q, void* points_host, uint64_t* found_host,
+                     void* neigh_host, uint8_t* paths_host, void* quot_host) {
+#define CALL(F) fri_query_export<F>(c, d_prev_poly, poly_stride, prev_len, d_prev_cw, prev_cw_stride, prev_domain, d_prev_nodes, d_next_cw, next_cw_stride, betas_host, q, points_host, found_host, neigh_host, paths_host, quot_host)
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }

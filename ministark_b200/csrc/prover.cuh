@@ -126,20 +126,21 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     }
     StageTimer tm(c, ps);
     IOPattern io = stark_iopattern(F::BITS, D, R, Q, QF);
-    Merlin merlin(io, c->bridge_masks);
-    const size_t cb = (F::BITS + 128) / 8;
-    auto challenge_base = [&](T* out) -> bool {
-        uint8_t buf[32];
-        if (!merlin.challenge_bytes(buf, cb)) return false;
-        *out = (T)be_bytes_mod(buf, cb, (uint64_t)F::P);
+    Merlin merlin(io, c->bridge_masks, c->leftover_as_published != 0);
+    auto challenge_base = [&](T* out) -> bool {  // let [x]: [F::Base; 1] = merlin.challenge_scalars()
+        uint64_t v;
+        if (!merlin.challenge_scalars(F::BITS, (uint64_t)F::P, 1, 1, &v)) return false;
+        *out = (T)v;
         return true;
     };
-    auto challenge_ext = [&](E* out) -> bool {
-        uint8_t buf[32 * 4];
-        if (!merlin.challenge_bytes(buf, cb * D)) return false;
-        for (int d = 0; d < D; d++) out->c[d] = (T)be_bytes_mod(buf + d * cb, cb, (uint64_t)F::P);
+    auto challenge_exts = [&](E* out, size_t count) -> bool {  // one fill_challenge_scalars call for `count` scalars
+        std::vector<uint64_t> v(count * D);
+        if (!merlin.challenge_scalars(F::BITS, (uint64_t)F::P, D, count, v.data())) return false;
+        for (size_t i = 0; i < count; i++)
+            for (int d = 0; d < D; d++) out[i].c[d] = (T)v[i * D + d];
         return true;
     };
+    auto challenge_ext = [&](E* out) -> bool { return challenge_exts(out, 1); };
 #define TR(expr) do { if (!(expr)) return fail(c, MS_ERR_TRANSCRIPT, "transcript pattern violated at %s", #expr); } while (0)
 
     // ---- 1.1 trace on the device (column-major) and its commitment           starks.rs:68-73
@@ -204,7 +205,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     // which holds for any polynomial with <= N coefficients, and carries the remainder (= mixed) on.
     // ---- 2. DEEP-ALI queries                                                         starks.rs:124-151
     std::vector<E> zq(Q);
-    for (uint64_t q = 0; q < Q; q++) TR(challenge_ext(&zq[q]));
+    TR(challenge_exts(zq.data(), Q));  // merlin.fill_challenge_scalars(&mut queries), starks.rs:124-125
     std::vector<E> opens(Q * (C + 1));
     tm.begin("deep_open");
     MS_TRY(eval_points<F>(c, coeffs.as<T>(), n, 0, 1, n, 1, C + 1, zq.data(), (int)Q, opens.data()));
@@ -274,7 +275,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     tm.end();
     // ---- FRI query phase                                                            fri.rs:115-189
     tm.begin("fri_query_phase");
-    std::vector<uint8_t> braw(8 * QF);
+    std::vector<uint8_t> braw(8 * QF, 0);  // vec![0u8; 8 * queries], fri.rs:121
     TR(merlin.challenge_bytes(braw.data(), braw.size()));                               // fri.rs:121-122
     std::vector<uint64_t> betas(QF);
     for (uint64_t k = 0; k < QF; k++) memcpy(&betas[k], &braw[8 * k], 8);               // usize::from_le_bytes
@@ -308,6 +309,16 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     struct PendingCopy { uint64_t at; const void* src; size_t bytes; };
     std::vector<PendingCopy> copies;
     cudaEvent_t dl[2] = {nullptr, nullptr};  // first / last proof-download copy on the copy stream (timing only)
+    // every exit path below (errors included) waits for the downloads already queued into proof_out and frees the events
+    struct CopyGuard {
+        Ctx* c;
+        cudaEvent_t* dl;
+        ~CopyGuard() {
+            cudaStreamSynchronize(c->copy_stream);
+            for (int i = 0; i < 2; i++)
+                if (dl[i]) { cudaEventDestroy(dl[i]); dl[i] = nullptr; }
+        }
+    } copy_guard{c, dl};
     uint64_t dl_bytes = 0;
     double q_host[4] = {0, 0, 0, 0};  // wall ms: look-ups + value search | neighbours, paths, quotients | serialise | enqueue copies
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -316,77 +327,26 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         FriRoundDev<F>& prev = rounds[i];
         FriRoundDev<F>& nxt = rounds[i + 1];
         const uint64_t nd = prev.domain;
-        const T g_prev = root_of_unity<F>(ilog2(nd)), g_next = root_of_unity<F>(ilog2(nxt.domain));
-        std::vector<unsigned long long> idx(3 * QF);
-        std::vector<T> x1(QF), x2(QF), x3(QF), s2(QF);
-        for (uint64_t k = 0; k < QF; k++) {
-            uint64_t beta = betas[k];
-            if (beta > nd) beta %= nd;                                                   // fri.rs:144 (strict >)
-            x1[k] = fpow<F>(g_prev, beta);                                               // fri.rs:148
-            x2[k] = fpow<F>(g_prev, nxt.domain + beta);                                  // fri.rs:149
-            x3[k] = fpow<F>(g_next, beta);                                               // fri.rs:150
-            s2[k] = F::mul(x1[k], x1[k]);
-            idx[3 * k] = beta % nd;
-            idx[3 * k + 1] = (nxt.domain + beta) % nd;
-            idx[3 * k + 2] = beta % nxt.domain;
-        }
-        // y1, y2 = prev.poly(x1), prev.poly(x2); y3 = round.poly(x3): evaluations at domain points are
-        // codeword entries (exact arithmetic), so they are gathered instead of re-evaluated.
-        Scratch d_idx(c), d_ys(c), d_found(c), d_neigh_idx(c), d_neigh(c), d_paths(c);
-        std::vector<E> ys(3 * QF);
-        const int path_len = ilog2(nd / 2);
-        std::vector<uint32_t> paths((size_t)2 * QF * path_len * 16);
-        std::vector<E> neigh(4 * QF);
         // A rank that only contributes quotient polynomials to a shared proof buffer (pw.mute) needs none of the
         // look-ups: they feed the fixed part, which rank 0 writes (sizes are data independent, so the offsets agree).
         const bool lookups = !pw.mute;
+        QueryLookups<F> lk;
         if (lookups) {
-        MS_TRY(d_idx.alloc(idx.size() * 8));
-        MS_TRY(d_ys.alloc(3 * QF * sizeof(E)));
-        {
-            // gather y1,y2 from prev.cw and y3 from nxt.cw: two launches over interleaved indices
-            std::vector<unsigned long long> i12(2 * QF), i3(QF);
-            for (uint64_t k = 0; k < QF; k++) { i12[2 * k] = idx[3 * k]; i12[2 * k + 1] = idx[3 * k + 1]; i3[k] = idx[3 * k + 2]; }
-            MS_TRY(stage_from_host(c, i12.data(), i12.size() * 8, d_idx.p));
-            MS_TRY(stage_from_host(c, i3.data(), i3.size() * 8, d_idx.as<unsigned long long>() + 2 * QF));
-            k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(prev.cw, prev.domain, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys.as<E>());
-            MS_LAUNCH_CHECK(c);
-            k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(nxt.cw, nxt.domain, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys.as<E>() + 2 * QF);
-            MS_LAUNCH_CHECK(c);
+            MS_TRY(fri_query_lookups<F>(c, prev.cw, prev.domain, nd, prev.nodes, nxt.cw, nxt.domain, nxt.domain, betas.data(), QF, &lk));
+            q_host[0] += now_ms() - t_q; t_q = now_ms();
+        } else {
+            const T g_prev = root_of_unity<F>(ilog2(nd));
+            lk.s2.resize(QF);
+            lk.path_len = ilog2(nd / 2);
+            for (uint64_t k = 0; k < QF; k++) {
+                uint64_t beta = betas[k];
+                if (beta > nd) beta %= nd;
+                const T x1 = fpow<F>(g_prev, beta);
+                lk.s2[k] = F::mul(x1, x1);
+            }
         }
-        // openings by value search: first leaf equal to y (merkle.rs:216-225), for y1 and y2 of each query
-        MS_TRY(d_found.alloc(2 * QF * 8));
-        MS_CUDA(c, cudaMemsetAsync(d_found.p, 0xff, 2 * QF * 8, c->stream));
-        k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(prev.cw, prev.domain, nd, d_ys.as<E>(), (int)(2 * QF), d_found.as<unsigned long long>());
-        MS_LAUNCH_CHECK(c);
-        std::vector<unsigned long long> found(2 * QF);
-        // small results go through mapped pinned memory, not the copy engine: a D2H copy here would queue
-        // behind the previous rounds' multi-MB quotient downloads and serialise this loop with the download
-        const size_t ys_bytes = 3 * QF * sizeof(E), found_bytes = 2 * QF * 8;
-        MS_TRY(stage_to_host(c, 0, d_ys.p, ys_bytes));
-        MS_TRY(stage_to_host(c, ys_bytes, d_found.p, found_bytes));
-        MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        memcpy(ys.data(), c->hstage, ys_bytes);
-        memcpy(found.data(), c->hstage + ys_bytes, found_bytes);
-        for (auto f : found)
-            if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
-        q_host[0] += now_ms() - t_q; t_q = now_ms();
-        std::vector<unsigned long long> nidx(4 * QF);
-        for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = found[k] & ~1ULL; nidx[2 * k + 1] = found[k] | 1ULL; }
-        MS_TRY(d_neigh_idx.alloc(nidx.size() * 8));
-        MS_TRY(d_neigh.alloc(4 * QF * sizeof(E)));
-        MS_TRY(d_paths.alloc((size_t)2 * QF * (path_len ? path_len : 1) * 64));
-        MS_TRY(stage_from_host(c, nidx.data(), nidx.size() * 8, d_neigh_idx.p));
-        k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(prev.cw, prev.domain, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh.as<E>());
-        MS_LAUNCH_CHECK(c);
-        if (path_len) {
-            int total = (int)(2 * QF) * path_len * 16;
-            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(prev.nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
-            MS_LAUNCH_CHECK(c);
-            MS_TRY(stage_to_host(c, 4 * QF * sizeof(E), d_paths.p, paths.size() * 4));
-        }
-        MS_TRY(stage_to_host(c, 0, d_neigh.p, 4 * QF * sizeof(E)));
-        }  // lookups
+        const std::vector<T>& s2 = lk.s2;
+        const int path_len = lk.path_len;
         // quotients (fri.rs:157-167): only the ones this rank downloads (all of them unless the download is sharded)
         const uint64_t nq = prev.len >= 3 ? prev.len - 2 : 0;
         T* d_quot = nullptr;
@@ -404,10 +364,11 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             }
         }
         MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (lookups) {
-            memcpy(neigh.data(), c->hstage, 4 * QF * sizeof(E));
-            if (path_len) memcpy(paths.data(), c->hstage + 4 * QF * sizeof(E), paths.size() * 4);
-        }
+        if (lookups) fri_query_lookups_finish<F>(c, QF, &lk);
+        else { lk.ys.assign(3 * QF, ext_zero<F>()); lk.neigh.assign(4 * QF, ext_zero<F>()); lk.paths.assign((size_t)2 * QF * path_len * 16, 0); lk.x1.assign(QF, 0); lk.x2.assign(QF, 0); lk.x3.assign(QF, 0); }
+        const std::vector<E>&ys = lk.ys, &neigh = lk.neigh;
+        const std::vector<uint32_t>& paths = lk.paths;
+        const std::vector<T>&x1 = lk.x1, &x2 = lk.x2, &x3 = lk.x3;
         q_host[1] += now_ms() - t_q; t_q = now_ms();
         // ---- serialise this round (fri.rs:18-22, merkle.rs:293-298)
         pw.u64(QF);
@@ -469,6 +430,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         ps->timings.emplace_back("(proof download GB)", (float)(dl_bytes * 1e-9));
         cudaEventDestroy(dl[0]);
         cudaEventDestroy(dl[1]);
+        dl[0] = dl[1] = nullptr;
     }
     if (!pw.fits()) {
         *proof_len = pw.pos;

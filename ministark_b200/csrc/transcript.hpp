@@ -3,9 +3,13 @@
 // parameter derivation of StarkConfig::new (src/starks.rs:268-332, src/util.rs:30-44).
 //
 // nimue's source is not in /root/reference: the sponge construction below follows SURVEY.md App. A
-// items 5-9 and is PARITY UNPINNED (no golden transcript exists); the three domain-separation bytes
-// are a Ctx switch.  Everything else in the prover is independent of it (challenges are inputs to
-// the device stages).
+// items 5-9 and is PARITY UNPINNED (no golden transcript exists).  Two details are Ctx switches
+// (ms_set_transcript_option): the three domain-separation bytes, and the handling of digest bytes left
+// over from the previous squeeze call -- nimue's leftovers branch, as published at 0e584985 (recalled),
+// reads `self.leftovers[..len].copy_from_slice(&output[..len])`: the copy runs the wrong way, the
+// leftovers are consumed but the caller's buffer keeps its old bytes.  That behaviour is the default
+// (leftover_as_published); the intended one (leftovers reach the output) is the alternative.
+// Everything else in the prover is independent of this file (challenges are inputs to the device stages).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -135,8 +139,10 @@ struct DigestBridge {
     uint64_t squeeze_i = 0;
     std::vector<uint8_t> leftovers;
     uint8_t mask_absorb = 0x00, mask_squeeze = 0x01, mask_squeeze_end = 0x02;
+    bool leftover_as_published = true;
 
-    void init(const uint8_t tag[32], const uint8_t masks[3]) {
+    void init(const uint8_t tag[32], const uint8_t masks[3], bool as_published = true) {
+        leftover_as_published = as_published;
         hasher.reset();
         memset(cv, 0, 32);
         mode = START;
@@ -189,6 +195,7 @@ struct DigestBridge {
         leftovers.clear();
         mode = START;
     }
+    // squeeze_unchecked(output): `out` arrives with the caller's previous contents (see the header)
     void squeeze(uint8_t* out, size_t n) {
         size_t got = 0;
         for (;;) {
@@ -203,7 +210,7 @@ struct DigestBridge {
                 return;
             } else if (!leftovers.empty()) {
                 size_t take = n - got < leftovers.size() ? n - got : leftovers.size();
-                memcpy(out + got, leftovers.data(), take);
+                if (!leftover_as_published) memcpy(out + got, leftovers.data(), take);
                 leftovers.erase(leftovers.begin(), leftovers.begin() + take);
                 got += take;
             } else {
@@ -266,10 +273,10 @@ struct Merlin {
     DigestBridge sponge;
     std::vector<uint8_t> transcript;  // absorbed bytes = StarkProof.arthur (src/starks.rs:160)
     bool ok = true;
-    Merlin(const IOPattern& io, const uint8_t masks[3]) : stack(io.ops) {
+    Merlin(const IOPattern& io, const uint8_t masks[3], bool leftover_as_published = true) : stack(io.ops) {
         uint8_t tag[32];
         nimue_tag(io.io, tag);
-        sponge.init(tag, masks);
+        sponge.init(tag, masks, leftover_as_published);
     }
     bool expect(char kind, size_t n) {
         if (stack.empty() || stack.front().first != kind || stack.front().second < n) {
@@ -287,11 +294,16 @@ struct Merlin {
         transcript.insert(transcript.end(), data, data + n);
         return true;
     }
+    // Merlin::fill_challenge_bytes: `out` keeps its previous contents where the sponge does not write
     bool challenge_bytes(uint8_t* out, size_t n) {
         if (!expect('S', n)) return false;
         sponge.squeeze(out, n);
         return true;
     }
+    // FieldChallenges::fill_challenge_scalars of nimue's ark plugin: ONE zero-initialised buffer of degree * cb
+    // bytes per call, refilled for every output scalar; coordinates big-endian mod p in tower order
+    // (`challenge_scalars::<1>()` is the same call with count = 1).  out: count * degree coordinates.
+    bool challenge_scalars(int bits, uint64_t p, int degree, size_t count, uint64_t* out);
 };
 
 // from_be_bytes_mod_order of a (bits+128)/8-byte challenge (App. A item 6)
@@ -299,6 +311,16 @@ inline uint64_t be_bytes_mod(const uint8_t* b, size_t n, uint64_t p) {
     unsigned __int128 acc = 0;
     for (size_t i = 0; i < n; i++) acc = ((acc << 8) | b[i]) % p;
     return (uint64_t)acc;
+}
+
+inline bool Merlin::challenge_scalars(int bits, uint64_t p, int degree, size_t count, uint64_t* out) {
+    const size_t cb = (size_t)(bits + 128) / 8;
+    uint8_t buf[4 * 32] = {0};
+    for (size_t i = 0; i < count; i++) {
+        if (!challenge_bytes(buf, cb * degree)) return false;
+        for (int d = 0; d < degree; d++) out[i * degree + d] = be_bytes_mod(buf + d * cb, cb, p);
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------- StarkConfig::new

@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
+#include <time.h>
 #include <pthread.h>
 #include "fields.h"
 
@@ -138,7 +140,59 @@ API u64 or_leaf_string(const u64 *elem, int deg, char *out) { return fmt_quad(el
  * `k` child digests) (:171-177), all nodes in level order in one vector (:119-140).
  * data: n_elems elements of `deg` coordinates each.  nodes_out may be NULL (root only).
  * Returns the node count, or -1 for the reference's panics (:93-104). */
-API int64_t or_merkle(const u64 *data, int deg, u64 n_elems, u64 lpn, u64 k, unsigned char *nodes_out, unsigned char *root_out) {
+/* ---- tiny pthread fan-out used by the multi-threaded legs (the reference itself is single-threaded) */
+static double or_now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+typedef void (*or_item_fn)(void *ctx, u64 item, int tid);
+typedef struct { or_item_fn fn; void *ctx; u64 n; u64 *next; pthread_mutex_t *mu; int tid; } or_pf_job;
+static void *or_pf_worker(void *p) {
+    or_pf_job *j = (or_pf_job *)p;
+    for (;;) {
+        pthread_mutex_lock(j->mu);
+        u64 i = (*j->next)++;
+        pthread_mutex_unlock(j->mu);
+        if (i >= j->n) break;
+        j->fn(j->ctx, i, j->tid);
+    }
+    return 0;
+}
+/* run fn(ctx, i) for i in [0, n) on up to `threads` pthreads (dynamic, one item at a time: items are coarse) */
+static void or_parallel_items(u64 n, int threads, or_item_fn fn, void *ctx) {
+    if (threads < 1) threads = 1;
+    if ((u64)threads > n) threads = (int)n;
+    if (threads <= 1) { for (u64 i = 0; i < n; i++) fn(ctx, i, 0); return; }
+    pthread_t *th = (pthread_t *)malloc(threads * sizeof(pthread_t));
+    or_pf_job *jobs = (or_pf_job *)malloc(threads * sizeof(or_pf_job));
+    pthread_mutex_t mu; pthread_mutex_init(&mu, 0);
+    u64 next = 0;
+    for (int t = 0; t < threads; t++) { jobs[t] = (or_pf_job){fn, ctx, n, &next, &mu, t}; pthread_create(&th[t], 0, or_pf_worker, &jobs[t]); }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], 0);
+    pthread_mutex_destroy(&mu);
+    free(th); free(jobs);
+}
+
+typedef struct { const u64 *data; int deg; u64 lpn, n1, chunk; unsigned char *nodes; } mk_leaf_job;
+static void mk_leaf_chunk(void *ctx, u64 ci, int tid) {
+    (void)tid;
+    mk_leaf_job *j = (mk_leaf_job *)ctx;
+    char s[512];
+    u64 g0 = ci * j->chunk, g1 = g0 + j->chunk; if (g1 > j->n1) g1 = j->n1;
+    for (u64 g = g0; g < g1; g++) {
+        sha256_ctx c; sha256_init(&c);
+        for (u64 e = 0; e < j->lpn; e++) {
+            size_t n = fmt_quad(j->data + (g * j->lpn + e) * j->deg, j->deg, s);
+            sha256_update(&c, s, n);
+        }
+        sha256_final(&c, j->nodes + 32 * g);
+    }
+}
+typedef struct { unsigned char *nodes; u64 k, src0, dst0, count, chunk; } mk_node_job;
+static void mk_node_chunk(void *ctx, u64 ci, int tid) {
+    (void)tid;
+    mk_node_job *j = (mk_node_job *)ctx;
+    u64 i0 = ci * j->chunk, i1 = i0 + j->chunk; if (i1 > j->count) i1 = j->count;
+    for (u64 i = i0; i < i1; i++) or_sha256(j->nodes + 32 * (j->src0 + i * j->k), 32 * j->k, j->nodes + 32 * (j->dst0 + i));
+}
+static int64_t or_merkle_mt(const u64 *data, int deg, u64 n_elems, u64 lpn, u64 k, unsigned char *nodes_out, unsigned char *root_out, int threads) {
     if (lpn == 0 || k < 2 || (k & (k - 1)) || n_elems % lpn) return -1;
     u64 n1 = n_elems / lpn;
     if (n1 == 0 || (n1 & (n1 - 1))) return -1;
@@ -148,24 +202,26 @@ API int64_t or_merkle(const u64 *data, int deg, u64 n_elems, u64 lpn, u64 k, uns
     u64 total = 0, lv = n1;
     for (unsigned l = 0; l < levels; l++) { total += lv; lv /= k; }
     unsigned char *nodes = nodes_out ? nodes_out : (unsigned char *)malloc(total * 32);
-    char *s = (char *)malloc(256);
-    for (u64 g = 0; g < n1; g++) {
-        sha256_ctx c; sha256_init(&c);
-        for (u64 e = 0; e < lpn; e++) {
-            size_t n = fmt_quad(data + (g * lpn + e) * deg, deg, s);
-            sha256_update(&c, s, n);
-        }
-        sha256_final(&c, nodes + 32 * g);
+    {
+        mk_leaf_job j = {data, deg, lpn, n1, 1024, nodes};
+        or_parallel_items((n1 + j.chunk - 1) / j.chunk, threads, mk_leaf_chunk, &j);
     }
-    free(s);
-    u64 src = 0, dst = n1;
+    /* inner levels in level order (src/merkle.rs:131-140): level l+1 hashes groups of k level-l digests */
+    u64 src = 0, dst = n1, cnt = n1 / k;
     while (dst < total) {
-        or_sha256(nodes + 32 * src, 32 * k, nodes + 32 * dst);
-        src += k; dst++;
+        mk_node_job j = {nodes, k, src, dst, cnt, 4096};
+        or_parallel_items((cnt + j.chunk - 1) / j.chunk, threads, mk_node_chunk, &j);
+        src += cnt * k; dst += cnt; cnt /= k;
     }
     if (root_out) memcpy(root_out, nodes + 32 * (total - 1), 32);
     if (!nodes_out) free(nodes);
     return (int64_t)total;
+}
+API int64_t or_merkle(const u64 *data, int deg, u64 n_elems, u64 lpn, u64 k, unsigned char *nodes_out, unsigned char *root_out) {
+    return or_merkle_mt(data, deg, n_elems, lpn, k, nodes_out, root_out, 1);
+}
+API int64_t or_merkle_threads(const u64 *data, int deg, u64 n_elems, u64 lpn, u64 k, unsigned char *nodes_out, unsigned char *root_out, int threads) {
+    return or_merkle_mt(data, deg, n_elems, lpn, k, nodes_out, root_out, threads);
 }
 
 /* ------------------------------------------------------------------ Keccak-f[1600] (for the nimue tag) */
@@ -282,4 +338,83 @@ API u64 or_fri_query_quotient(int field, const u64 *poly, u64 n, u64 x1, u64 x2,
     if (field == 0) { gl_ext a, b; memcpy(&a, y1, sizeof a); memcpy(&b, y2, sizeof b); return gl_fri_query_quotient((const gl_ext *)poly, n, x1, x2, a, b, (gl_ext *)q); }
     bb_ext a, b; memcpy(&a, y1, sizeof a); memcpy(&b, y2, sizeof b);
     return bb_fri_query_quotient((const bb_ext *)poly, n, x1, x2, a, b, (bb_ext *)q);
+}
+
+/* ------------------------------------------------------------------ transcript + whole prover / verifier */
+#include "transcript.inc"
+
+#define PFX(x) gl_##x
+#define F_P GL_P
+#define F_ROOT GL_ROOT
+#define F_TWO_ADICITY GL_TWO_ADICITY
+#define EXT_D 2
+#define F_BITS 64
+#define F_SER 8
+#define F_ID 0
+#include "prover.inc"
+#undef PFX
+#undef F_P
+#undef F_ROOT
+#undef F_TWO_ADICITY
+#undef EXT_D
+#undef F_BITS
+#undef F_SER
+#undef F_ID
+
+#define PFX(x) bb_##x
+#define F_P BB_P
+#define F_ROOT BB_ROOT
+#define F_TWO_ADICITY BB_TWO_ADICITY
+#define EXT_D 4
+#define F_BITS 31
+#define F_SER 4
+#define F_ID 1
+#include "prover.inc"
+#undef PFX
+#undef F_P
+#undef F_ROOT
+#undef F_TWO_ADICITY
+#undef EXT_D
+#undef F_BITS
+#undef F_SER
+#undef F_ID
+
+/* Stark::prove (src/starks.rs:59-169).  trace_rm: row-major N x W canonical elements (uint64 for both fields),
+ * cmat: T x W.  stage_ms (optional): 8 doubles, see OR_T_*.  Returns the proof length or a negative error. */
+API int64_t or_stark_prove(int field, const or_stark_params *p, const u64 *trace_rm, u64 N, u64 W, const u64 *cmat, u64 T,
+                           unsigned char *out, u64 cap, int threads, double *stage_ms) {
+    return field == 0 ? gl_stark_prove(p, trace_rm, N, W, cmat, T, out, cap, threads, stage_ms)
+                      : bb_stark_prove(p, trace_rm, N, W, cmat, T, out, cap, threads, stage_ms);
+}
+/* upper bound of the proof dump for an n x cols problem (same formula as ms_stark_proof_bound) */
+API u64 or_stark_proof_bound(int field, const or_stark_params *p, u64 n, u64 cols) {
+    u64 R, Q, QF;
+    if (or_stark_derive(field, p, &R, &Q, &QF)) return 0;
+    const u64 E = field == 0 ? 16 : 16;
+    u64 sz = 8 + 8 + 8 + 64 * R + 64 + 16 + Q * cols * E + 8 + Q * E + 8;
+    u64 npad = n, domain = n * p->blowup_factor;
+    for (u64 i = 0; i + 1 < R; i++) {
+        u64 path_len = 0; while ((2ULL << path_len) < domain) path_len++;
+        if (domain < 2) path_len = 0;
+        u64 per_q = 6 * E + 2 * (8 + 2 * E + 8 + path_len * (8 + 64)) + 8 + npad * E;
+        sz += 8 + QF * per_q;
+        npad = npad > 1 ? npad / 2 : 1;
+        domain /= 2;
+    }
+    return sz;
+}
+/* Stark::verify (src/starks.rs:171-235): coeffs = the Constrains polynomials, poly-major [C][N]. */
+API int or_stark_verify(int field, const or_stark_params *p, const u64 *coeffs, u64 N, u64 C, const unsigned char *proof, u64 len,
+                        int strict, int *why) {
+    return field == 0 ? gl_stark_verify(p, coeffs, N, C, proof, len, strict, why) : bb_stark_verify(p, coeffs, N, C, proof, len, strict, why);
+}
+/* the Constrains object of TraceTable::derive_constrains (src/air.rs:127-144) for a linear AIR: [W + T][N] */
+API void or_derive_constrains(int field, const u64 *trace_rm, u64 N, u64 W, const u64 *cmat, u64 T, u64 *out_cm, int threads) {
+    if (field == 0) {
+        gl_intt_job a = {trace_rm, N, W, out_cm}; or_parallel_items(W, threads, gl_intt_item, &a);
+        gl_cons_job b = {NULL, N, W, T, cmat, out_cm}; or_parallel_items(T, threads, gl_cons_item, &b);
+    } else {
+        bb_intt_job a = {trace_rm, N, W, out_cm}; or_parallel_items(W, threads, bb_intt_item, &a);
+        bb_cons_job b = {NULL, N, W, T, cmat, out_cm}; or_parallel_items(T, threads, bb_cons_item, &b);
+    }
 }

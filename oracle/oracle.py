@@ -22,7 +22,7 @@ EXT_DEGREE = {GL: 2, BB: 4}
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the Makefile next to this file (gcc only)."""
-    srcs = [os.path.join(_DIR, f) for f in ("oracle.c", "oracle_impl.inc", "fields.h")]
+    srcs = [os.path.join(_DIR, f) for f in ("oracle.c", "oracle_impl.inc", "prover.inc", "transcript.inc", "fields.h")]
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs if os.path.exists(s)
     ):
@@ -63,6 +63,15 @@ def lib():
             "or_fri_codeword": (None, [i32, vp, u64, u64, vp]),
             "or_fri_fold": (u64, [i32, vp, u64, vp, vp, vp, vp]),
             "or_fri_query_quotient": (u64, [i32, vp, u64, u64, u64, vp, vp, vp]),
+            "or_merkle_threads": (C.c_int64, [vp, i32, u64, u64, u64, vp, vp, i32]),
+            "or_set_bridge_masks": (None, [i32, i32, i32]),
+            "or_set_leftover_mode": (None, [i32]),
+            "or_stark_derive": (i32, [i32, vp, vp, vp, vp]),
+            "or_transcript_squeeze_test": (C.c_int64, [i32, u64, u64, u64, vp, u64, vp]),
+            "or_stark_prove": (C.c_int64, [i32, vp, vp, u64, u64, vp, u64, vp, u64, i32, vp]),
+            "or_stark_verify": (i32, [i32, vp, vp, u64, u64, vp, u64, i32, vp]),
+            "or_derive_constrains": (None, [i32, vp, u64, u64, vp, u64, vp, i32]),
+            "or_stark_proof_bound": (u64, [i32, vp, u64, u64]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -215,3 +224,87 @@ def fri_query_quotient(field, poly, x1: int, x2: int, y1, y2) -> np.ndarray:
     q = np.zeros((max(poly.shape[0], 1), D), dtype=np.uint64)
     n = lib().or_fri_query_quotient(field, _p(poly), poly.shape[0], x1, x2, _p(y1), _p(y2), _p(q))
     return q[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------- whole prover
+class StarkParams(C.Structure):
+    """StarkConfig::new arguments (starks.rs:268-273) + the inner_children extension; same layout as ms_stark_params."""
+
+    _fields_ = [(n, C.c_uint64) for n in ("security_bits", "blowup_factor", "steps", "trace_columns", "inner_children")]
+
+
+STAGES = ("trace_commit", "intt+constraints", "lde", "lde_commit", "mix+open", "fri_commit_phase", "fri_query_phase", "total")
+PROVE_ERRORS = {-1: "bad shape (reference panics)", -3: "transcript pattern violated", -4: "leaf is not included in the tree",
+                -5: "random_shift is zero"}
+
+
+def set_leftover_mode(as_published: bool) -> None:
+    lib().or_set_leftover_mode(int(as_published))
+
+
+def set_bridge_masks(absorb: int, squeeze: int, squeeze_end: int) -> None:
+    lib().or_set_bridge_masks(absorb, squeeze, squeeze_end)
+
+
+def stark_derive(field: int, security_bits: int, blowup: int, steps: int):
+    p = StarkParams(security_bits, blowup, steps, 1, 2)
+    r, cq, fq = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    if lib().or_stark_derive(field, C.byref(p), C.byref(r), C.byref(cq), C.byref(fq)):
+        raise ValueError("bad STARK parameters")
+    return r.value, cq.value, fq.value
+
+
+def stark_prove(field: int, security_bits: int, blowup: int, steps: int, trace_columns: int, trace_rm, matrix,
+                inner_children: int = 2, threads: int = 1, want_timings: bool = False):
+    """Stark::prove (starks.rs:59-169) in C: returns the canonical proof bytes (and the per-stage wall ms)."""
+    t = _u64(trace_rm)
+    N, W = t.shape
+    m = _u64(matrix).reshape(-1, W) if np.size(matrix) else np.zeros((0, W), dtype=np.uint64)
+    p = StarkParams(security_bits, blowup, steps, trace_columns, inner_children)
+    ms = (C.c_double * len(STAGES))()
+    bound = lib().or_stark_proof_bound(field, C.byref(p), N, W + m.shape[0])
+    if bound == 0:
+        raise ValueError(PROVE_ERRORS[-1])
+    buf = np.empty(bound, dtype=np.uint8)
+    got = lib().or_stark_prove(field, C.byref(p), _p(t), N, W, _p(m), m.shape[0], _p(buf), bound, threads, ms)
+    if got < 0:
+        raise ValueError(PROVE_ERRORS.get(got, f"or_stark_prove: {got}"))
+    assert got <= bound
+    buf = buf[:got]
+    return (buf, dict(zip(STAGES, ms))) if want_timings else buf
+
+
+def stark_prove_into(field: int, params: "StarkParams", trace_rm, matrix, out: np.ndarray, threads: int = 1):
+    """single pass into a caller buffer (bench: no sizing pass); returns (length, stage ms)"""
+    t = _u64(trace_rm)
+    N, W = t.shape
+    m = _u64(matrix).reshape(-1, W)
+    ms = (C.c_double * len(STAGES))()
+    got = lib().or_stark_prove(field, C.byref(params), _p(t), N, W, _p(m), m.shape[0], _p(out), out.size, threads, ms)
+    if got < 0:
+        raise ValueError(PROVE_ERRORS.get(got, f"or_stark_prove: {got}"))
+    return got, dict(zip(STAGES, ms))
+
+
+def derive_constrains(field: int, trace_rm, matrix, threads: int = 1) -> np.ndarray:
+    """TraceTable::derive_constrains (air.rs:127-144) for a linear AIR: [W + T, N] coefficient vectors."""
+    t = _u64(trace_rm)
+    N, W = t.shape
+    m = _u64(matrix).reshape(-1, W)
+    out = np.zeros((W + m.shape[0], N), dtype=np.uint64)
+    lib().or_derive_constrains(field, _p(t), N, W, _p(m), m.shape[0], _p(out), threads)
+    return out
+
+
+def stark_verify(field: int, security_bits: int, blowup: int, steps: int, trace_columns: int, constrains_cm, proof,
+                 inner_children: int = 2, strict: bool = True):
+    """Stark::verify (starks.rs:171-235) in C.  Returns (accepted, line of the failed check or 0)."""
+    c = _u64(constrains_cm)
+    Cn, N = c.shape
+    pr = np.frombuffer(bytes(proof), dtype=np.uint8) if not isinstance(proof, np.ndarray) else np.ascontiguousarray(proof, dtype=np.uint8)
+    p = StarkParams(security_bits, blowup, steps, trace_columns, inner_children)
+    why = C.c_int(0)
+    r = lib().or_stark_verify(field, C.byref(p), _p(c), N, Cn, _p(pr), pr.size, int(strict), C.byref(why))
+    if r < 0:
+        raise ValueError(f"malformed proof dump ({r})")
+    return bool(r), why.value

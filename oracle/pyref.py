@@ -12,6 +12,7 @@ switch so it can be flipped the day a golden vector exists:
   ZERO_DISPLAY      Display of the zero field element ("0" in ark-ff 0.5.0, "" in 0.4.x)
   EXT_DISPLAY_FMT   Display of QuadExtField ("QuadExtField({} + {} * u)")
   BRIDGE_MASKS      nimue DigestBridge domain-separation block prefixes (absorb, squeeze, squeeze_end)
+  LEFTOVER_AS_PUBLISHED  nimue DigestBridge leftover handling (wrong-way copy as published vs intended)
   test_rng / fp_rand  ark-std test_rng seed + rand 0.8 StdRng (ChaCha12) + ark-ff Fp::rand
 Everything else (field arithmetic, NTT/LDE values, tree shape, SHA-256, fold, exact division) has
 exactly one correct answer and is pinned by mathematics / FIPS 180-4.
@@ -27,6 +28,11 @@ from typing import Callable, List, Optional, Sequence, Tuple
 ZERO_DISPLAY = "0"
 EXT_DISPLAY_FMT = "QuadExtField({} + {} * u)"
 BRIDGE_MASKS = {"absorb": 0x00, "squeeze": 0x01, "squeeze_end": 0x02}
+# nimue@0e584985 src/hash/legacy.rs, leftovers branch of DigestBridge::squeeze_unchecked, as published (recalled):
+#     self.leftovers[..len].copy_from_slice(&output[..len]);   // the copy runs the wrong way
+# i.e. digest bytes left over from the previous squeeze call are consumed (and counted by squeeze_end) but never
+# reach the caller, whose buffer keeps what it held.  True = restate that; False = the intended behaviour.
+LEFTOVER_AS_PUBLISHED = True
 
 
 # --------------------------------------------------------------------------- util.rs
@@ -124,14 +130,16 @@ class StarkField:
     def ext_mul(self, a, b):
         if self.ext_degree == 2:  # Goldilocks: u^2 = 7 (field.rs:55)
             return self._fp2_mul(a, b, 7)
-        # BabyBear: u^2 = 11 (field.rs:84), v^2 = u + 2013265910 = u - 11 (field.rs:96)
+        # BabyBear: u^2 = 11 (field.rs:84).  Effective quartic tower: v^2 = u.  ark-ff 0.5.0's QuadExtField
+        # mul/square/inverse reduce with Fp4Config::mul_fp2_by_nonresidue_in_place, whose default body is
+        # (c0, c1) -> (11 c1, c0) = multiplication by u; the reference does not override it, so the declared
+        # NONRESIDUE (2013265910, 1) of field.rs:96 is never read, and the declared Frobenius coefficients
+        # 11^((q^i-1)/4) (field.rs:98-107) are those of v^4 = 11.  [recalled: ark-ff is not in the image]
         p = self.p
         a0, a1, b0, b1 = a[0:2], a[2:4], b[0:2], b[2:4]
-        xi = (p - 11, 1)
         a0b0 = self._fp2_mul(a0, b0, 11)
         a1b1 = self._fp2_mul(a1, b1, 11)
-        t = self._fp2_mul(a1b1, xi, 11)
-        c0 = ((a0b0[0] + t[0]) % p, (a0b0[1] + t[1]) % p)
+        c0 = ((a0b0[0] + 11 * a1b1[1]) % p, (a0b0[1] + a1b1[0]) % p)
         x = self._fp2_mul(a0, b1, 11)
         y = self._fp2_mul(a1, b0, 11)
         c1 = ((x[0] + y[0]) % p, (x[1] + y[1]) % p)
@@ -450,8 +458,10 @@ class DigestBridge:
         self.leftovers = b""
         self.mode = ("start", 0)
 
-    def squeeze(self, n: int) -> bytes:
-        out = b""
+    def squeeze_into(self, out: bytearray) -> None:
+        """squeeze_unchecked(output): `out` arrives with the caller's previous contents, which survive where the
+        published leftovers branch fails to overwrite them (LEFTOVER_AS_PUBLISHED)."""
+        n, got = len(out), 0
         while True:
             if self.mode[0] == "start":
                 self.mode = ("squeeze", 0)
@@ -459,21 +469,29 @@ class DigestBridge:
                 self.hasher.update(self.cv)
             elif self.mode[0] == "absorb":
                 self.ratchet()
-            elif len(out) == n:
-                return out
+            elif got == n:
+                return
             elif self.leftovers:
-                take = min(n - len(out), len(self.leftovers))
-                out += self.leftovers[:take]
+                take = min(n - got, len(self.leftovers))
+                if not LEFTOVER_AS_PUBLISHED:
+                    out[got : got + take] = self.leftovers[:take]
                 self.leftovers = self.leftovers[take:]
+                got += take
             else:
                 i = self.mode[1]
                 h = self.hasher.copy()
                 h.update(struct.pack(">Q", i))
                 digest = h.digest()
-                take = min(n - len(out), self.OUT)
-                out += digest[:take]
+                take = min(n - got, self.OUT)
+                out[got : got + take] = digest[:take]
                 self.leftovers += digest[take:]
+                got += take
                 self.mode = ("squeeze", i + 1)
+
+    def squeeze(self, n: int) -> bytes:
+        out = bytearray(n)
+        self.squeeze_into(out)
+        return bytes(out)
 
 
 class IOPattern:
@@ -597,19 +615,36 @@ class Transcript:
         return [deserialize_ext(F, raw[i * per : (i + 1) * per]) for i in range(count)]
 
     # both
+    def fill_challenge_bytes(self, buf: bytearray) -> None:
+        self._expect("S", len(buf))
+        self.sponge.squeeze_into(buf)
+
     def challenge_bytes(self, n: int) -> bytes:
-        self._expect("S", n)
-        return self.sponge.squeeze(n)
+        buf = bytearray(n)  # callers pass a zero-initialised vector (fri.rs:121)
+        self.fill_challenge_bytes(buf)
+        return bytes(buf)
 
-    def challenge_base(self) -> int:
-        n = bytes_uniform_modp(self.F.modulus_bits)
-        return int.from_bytes(self.challenge_bytes(n), "big") % self.F.p  # from_be_bytes_mod_order
-
-    def challenge_ext(self) -> tuple:
+    def fill_challenge_scalars(self, count: int, degree: int) -> List[tuple]:
+        """nimue ark plugin FieldChallenges::fill_challenge_scalars: ONE zero-initialised buffer of degree*cb bytes
+        per call, refilled for each output scalar (so a scalar can inherit bytes of the previous one where the
+        published leftovers branch does not write)."""
         F = self.F
         n = bytes_uniform_modp(F.modulus_bits)
-        buf = self.challenge_bytes(F.ext_degree * n)
-        return tuple(int.from_bytes(buf[i * n : (i + 1) * n], "big") % F.p for i in range(F.ext_degree))
+        buf = bytearray(degree * n)
+        out = []
+        for _ in range(count):
+            self.fill_challenge_bytes(buf)
+            out.append(tuple(int.from_bytes(buf[i * n : (i + 1) * n], "big") % F.p for i in range(degree)))
+        return out
+
+    def challenge_base(self) -> int:  # let [x]: [F::Base; 1] = merlin.challenge_scalars()
+        return self.fill_challenge_scalars(1, 1)[0][0]
+
+    def challenge_ext(self) -> tuple:  # let [z]: [F; 1] = transcript.challenge_scalars()
+        return self.fill_challenge_scalars(1, self.F.ext_degree)[0]
+
+    def challenge_ext_many(self, count: int) -> List[tuple]:  # merlin.fill_challenge_scalars(&mut queries)
+        return self.fill_challenge_scalars(count, self.F.ext_degree)
 
 
 def serialize_ext(F: StarkField, x) -> bytes:
@@ -1023,7 +1058,7 @@ class Stark:  # starks.rs:30-236
         # QUOTIENT is zero (deg < N) and carries the remainder (= mixed) on as "validity_poly".
         assert len(mixed) <= trace_domain.size, "starks.rs:119 assert_eq!(rest, zero)"
         validity_poly = mixed
-        queries = [merlin.challenge_ext() for _ in range(cfg.constrain_queries)]  # :124-125
+        queries = merlin.challenge_ext_many(cfg.constrain_queries)  # :124-125 (one fill_challenge_scalars call)
         ext_validity = [F.ext_from_base(c) for c in validity_poly]  # :132
         ext_polys = [[F.ext_from_base(c) for c in p] for p in constrains.get_polynomials()]  # :133-137
         constrain_queries = [[poly_eval_ext(F, p, q) for p in ext_polys] for q in queries]  # :140-146
@@ -1044,7 +1079,7 @@ class Stark:  # starks.rs:30-236
         domain = Domain.new(F, cfg.degree + 1)  # :190
         assert arthur.next_bytes(32) == proof.constrain_trace_commit  # :191
         r = arthur.challenge_base()  # :193
-        queries = [arthur.challenge_ext() for _ in range(cfg.constrain_queries)]  # :198-199
+        queries = arthur.challenge_ext_many(cfg.constrain_queries)  # :198-199
         ext_cons = [[F.ext_from_base(c) for c in p] for p in constrains.get_polynomials()]  # :204-208
         for q, cq, vq in zip(queries, proof.constrain_queries, proof.validity_queries):  # :209-225
             c_x: List[tuple] = []

@@ -34,10 +34,16 @@ def test_linear_constraints_and_mix(field, n, w, ctxs, oracle):
     coeffs = rand_field(field, (w, n), n + w)
     m = synth_linear_matrix(field, n, w)
     got = ctx.to_host(ctx.linear_constraints(ctx.to_device(coeffs), m))
-    for t in range(w):
-        want = np.array([(int(m[t, t]) * int(a) + int(m[t, (t + 1) % w]) * int(b)) % p
-                         for a, b in zip(coeffs[t][:64], coeffs[(t + 1) % w][:64])], dtype=np.uint64)
-        assert (got[t][:64] == want).all()
+    for t in range(w):  # every coefficient, exact big-int arithmetic
+        want = (int(m[t, t]) * coeffs[t].astype(object) + int(m[t, (t + 1) % w]) * coeffs[(t + 1) % w].astype(object)) % p
+        assert (got[t].astype(object) == want).all()
+    # the same columns through the C oracle's derive_constrains-style accumulation (dense matrix, incl. zero entries)
+    dense = rand_field(field, (3, w), 17)
+    dense[1, :] = 0
+    got_d = ctx.to_host(ctx.linear_constraints(ctx.to_device(coeffs), dense))
+    for t in range(3):
+        want = sum(int(dense[t, j]) * coeffs[j].astype(object) for j in range(w)) % p
+        assert (got_d[t].astype(object) == want).all()
     # e2e_goldilocks.rs:57-59 style row with three non-zeros
     m2 = np.zeros((1, w), dtype=np.uint64)
     m2[0, :3] = [p - 1, p - 1, 1]
