@@ -222,6 +222,39 @@ typedef struct ms_commit_hooks {
 int32_t ms_stark_prove_hooked(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
                               const void* constraint_matrix_host, uint64_t t, const ms_commit_hooks* hooks,
                               uint8_t* proof_out, uint64_t* proof_len);
+/* ---- multi-GPU inside the library (csrc/comm.cuh, csrc/prover.cuh) ----------------------------------------
+ * One prover replica per GPU.  Bind every rank's context to a communicator, then call ms_stark_prove_multi (or any
+ * ms_stark_prove*) on all ranks with the same arguments: the trace tree, iNTT, constraints, LDE + its tree, mixing, DEEP
+ * openings, the large FRI round trees and the proof download are split over the ranks inside the call; proofs are byte-identical
+ * for every number of ranks.  Two backends:
+ *   NCCL  (one process per GPU): rank 0 makes a 128-byte id with ms_comm_unique_id, the host distributes it by any means
+ *         (MPI, a file, torch.distributed), every rank calls ms_comm_init_nccl.  libnccl.so.2 is dlopen'ed (the copy already
+ *         loaded in the process, if any; MINISTARK_NCCL_LIB overrides); failures return MS_ERR_NCCL.  Bulk data never goes
+ *         through NCCL: kernels read the peers' buffers over NVLink (CUDA IPC); NCCL carries barriers and 32-byte digests.
+ *   local (one process, one host thread per rank): ms_comm_init_local binds `world` contexts (same or different devices;
+ *         several ranks may share one GPU) into a group; each context must then be driven by its own thread.
+ * No reference call site: the reference is single-threaded (README.md:33). */
+int32_t ms_comm_unique_id(uint8_t id128[128]);
+int32_t ms_comm_init_nccl(ms_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t world);
+int32_t ms_comm_init_local(ms_ctx* const* ctxs, int32_t world);
+int32_t ms_comm_destroy(ms_ctx* ctx); /* collective */
+int32_t ms_comm_info(const ms_ctx* ctx, int32_t* rank, int32_t* world, const char** backend);
+/* which stages shard (default MS_SHARD_ALL); the proof does not depend on it */
+enum { MS_SHARD_TRACE_TREE = 1, MS_SHARD_COLUMNS = 2, MS_SHARD_FRI_TREES = 4, MS_SHARD_DOWNLOAD = 8, MS_SHARD_ALL = 15 };
+int32_t ms_set_shard_mask(ms_ctx* ctx, int32_t mask);
+/* the split the library uses, for hosts that want to size buffers (and for tests): [a, b) = rank's share of `cols` columns;
+ * per_rank / left = leaf groups per rank and digests each rank contributes for a tree of `groups` leaf groups with arity k
+ * (returns MS_ERR_BAD_SHAPE when the tree does not split over `world` ranks: the library then builds it on every rank). */
+int32_t ms_shard_plan(uint64_t cols, uint64_t groups, uint64_t k, int32_t world, int32_t rank, uint64_t* a, uint64_t* b,
+                      uint64_t* per_rank, uint64_t* left);
+/* flags of ms_stark_prove_multi: MS_PROOF_SHARED = proof_out is ONE host buffer shared by all ranks (shm / the same pointer),
+ * page-locked in every process (ms_host_register): every rank downloads its share of the quotient polynomials to the final
+ * offsets, rank 0 writes the rest, and the call returns on every rank when the proof is complete.  Without it rank 0 gets the
+ * proof (all ranks with MS_PROOF_ALL_RANKS) and the other ranks may pass proof_out = NULL. */
+enum { MS_PROOF_SHARED = 1, MS_PROOF_ALL_RANKS = 2 };
+int32_t ms_stark_prove_multi(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
+                             const void* constraint_matrix_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len, int32_t flags);
+
 /* Upper levels of a tree whose level-`n` digests already exist (8 words each, device): hashes groups of
  * `inner_children` digests until one is left (src/merkle.rs:133-140).  Used to join the subtree roots
  * the ranks gathered.  n must be a power of inner_children. */

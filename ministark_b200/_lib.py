@@ -72,6 +72,14 @@ SIGNATURES = {
     "ms_stark_prove": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_device": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_hooked": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
+    "ms_comm_unique_id": (_i32, [_vp]),
+    "ms_comm_init_nccl": (_i32, [_vp, _vp, _i32, _i32]),
+    "ms_comm_init_local": (_i32, [C.POINTER(_vp), _i32]),
+    "ms_comm_destroy": (_i32, [_vp]),
+    "ms_comm_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_char_p)]),
+    "ms_set_shard_mask": (_i32, [_vp, _i32]),
+    "ms_shard_plan": (_i32, [_u64, _u64, _u64, _i32, _i32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "ms_stark_prove_multi": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64), _i32]),
     "ms_merkle_subtree": (_i32, [_vp, _vp, _u64, _u64, _u64, _i32, _u64, _u64, _vp, C.POINTER(_u64)]),
     "ms_merkle_reduce": (_i32, [_vp, _vp, _u64, _u64, _vp]),
     "ms_merkle_subtree_gather": (_i32, [_vp, _vp, _u64, _u64, _i32, _u64, _u64, _vp, C.POINTER(_u64)]),

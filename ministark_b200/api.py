@@ -50,6 +50,8 @@ class Context:
             ops = getattr(self, "_sharded_ops", None)
             if ops is not None:
                 ops.close_peers()  # unmap / free the CUDA-IPC exchange buffers (all device work is done by now)
+            # a communicator still bound here is dropped without the collective teardown (call comm_destroy on every
+            # rank first for an orderly one)
             self.lib.ms_ctx_destroy(self.h)
             self.h = None
 
@@ -264,6 +266,52 @@ class Context:
         cap = C.c_uint64(out.size)
         self._check(self.lib.ms_stark_prove_device(self.h, C.byref(params), self._ptr(trace_cm), n, w, m.ctypes.data, m.shape[0],
                                                    out.ctypes.data, C.byref(cap)))
+        return int(cap.value)
+
+    # ---------------------------------------------------------------- multi-GPU (csrc/comm.cuh)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id made by rank 0; distribute it to the other ranks by any means."""
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.load().ms_comm_unique_id(buf)
+        if rc != 0:
+            raise MiniStarkError(rc, "ms_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init_nccl(self, unique_id: bytes, rank: int, world: int):
+        """one process per GPU: collective over all ranks"""
+        buf = (C.c_uint8 * 128)(*unique_id)
+        self._check(self.lib.ms_comm_init_nccl(self.h, buf, rank, world))
+
+    @staticmethod
+    def comm_init_local(ctxs: Sequence["Context"]):
+        """one process, one host thread per rank: binds the contexts into a group (rank = position in the list)"""
+        arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        rc = _lib.load().ms_comm_init_local(arr, len(ctxs))
+        if rc != 0:
+            raise MiniStarkError(rc, "ms_comm_init_local failed")
+
+    def comm_destroy(self):
+        self._check(self.lib.ms_comm_destroy(self.h))
+
+    def comm_info(self) -> Tuple[int, int, str]:
+        r, w, b = C.c_int32(), C.c_int32(), C.c_char_p()
+        self.lib.ms_comm_info(self.h, C.byref(r), C.byref(w), C.byref(b))
+        return r.value, w.value, b.value.decode()
+
+    def set_shard_mask(self, mask: int):
+        self._check(self.lib.ms_set_shard_mask(self.h, mask))
+
+    def stark_prove_multi(self, params: StarkParams, trace_cm, constraint_matrix: np.ndarray, out: Optional[np.ndarray],
+                          shared: bool = False, all_ranks: bool = False) -> int:
+        """ms_stark_prove_multi on this rank (every rank of the communicator must call it).  out: host uint8 buffer
+        (one buffer shared by all ranks with shared=True; may be None on ranks > 0 otherwise).  Returns the proof length."""
+        w, n = trace_cm.shape
+        m = np.ascontiguousarray(constraint_matrix, dtype=self.np_dtype).reshape(-1, w)
+        cap = C.c_uint64(out.size if out is not None else 0)
+        flags = (1 if shared else 0) | (2 if all_ranks else 0)
+        self._check(self.lib.ms_stark_prove_multi(self.h, C.byref(params), self._ptr(trace_cm), n, w, m.ctypes.data, m.shape[0],
+                                                  out.ctypes.data if out is not None else None, C.byref(cap), flags))
         return int(cap.value)
 
     def last_timings(self):

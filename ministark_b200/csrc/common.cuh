@@ -12,6 +12,8 @@
 
 namespace ms {
 
+struct Comm;  // comm.cuh
+
 struct Ctx {
     int field = 0;
     int device = 0;
@@ -38,6 +40,9 @@ struct Ctx {
     // transcript switches (host prover)
     uint8_t bridge_masks[3] = {0x00, 0x01, 0x02};
     int leftover_as_published = 1;  // nimue DigestBridge leftovers branch as published (see transcript.hpp)
+    // multi-GPU: the communicator this context is a rank of (nullptr: single GPU) and which stages shard
+    Comm* comm = nullptr;
+    int shard_mask = MS_SHARD_ALL;
 };
 
 inline int fail(Ctx* c, int code, const char* fmt, ...) {

@@ -40,9 +40,8 @@ int fri_deep_coeffs(Ctx* c, const typename F::T* d_poly, uint64_t stride, uint64
                     typename F::T* d_out_host) {
     Ext<F> z = ext_from_host<F>(z_host);
     Ext<F>* out = reinterpret_cast<Ext<F>*>(d_out_host);
-    MS_TRY(eval_points<F>(c, d_poly, stride, 0, 2, (n + 1) / 2, F::D, 1, &z, 1, &out[0]));
-    MS_TRY(eval_points<F>(c, d_poly, stride, 1, 2, n / 2, F::D, 1, &z, 1, &out[1]));
-    return MS_OK;
+    // both halves in one pass: polynomial p (0 = even, 1 = odd) is the subsequence off = p, step = 2 of the same planes
+    return eval_points<F>(c, d_poly, stride, 0, 2, (n + 1) / 2, F::D, 2, &z, 1, out, /*poly_off=*/1, /*shared_planes=*/true, /*limit=*/n);
 }
 
 // a10.  element i of the folded, DEEP-adjusted sequence
@@ -175,6 +174,33 @@ __global__ void k_gather_paths(const uint32_t* __restrict__ nodes, uint64_t n_gr
     out[tid] = nodes[(off + pair) * 8 + w];
 }
 
+// The same for a tree whose nodes are spread over the ranks (row-sharded FRI tree, prover.cuh): level l holds
+// n_groups >> l digests; while that is more than `world`, rank g owns the contiguous share g of the level, stored in
+// its arena at arena_off in local level order (n_groups/world, n_groups/(2 world), ..., 1 digests); the levels from
+// `world` digests upward are replicated in `top` (world, world/2, ..., 1 digests).  Peer digests come over NVLink.
+__global__ void k_gather_paths_sharded(PeerTable arenas, uint64_t arena_off, int world, const uint32_t* __restrict__ top,
+                                       uint64_t n_groups, int path_len, const unsigned long long* __restrict__ leaf_idx, int nt,
+                                       uint32_t* __restrict__ out) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int per = path_len * 16;
+    if (tid >= nt * per) return;
+    int k = tid / per, rem = tid % per, l = rem / 16, w = rem % 16;
+    const uint64_t node = (uint64_t)(leaf_idx[k] >> 1) >> l, pair = node & ~1ULL, idx = pair + (uint64_t)(w >> 3);
+    const uint64_t lv = n_groups >> l;
+    uint32_t v;
+    if (lv > (uint64_t)world) {
+        const uint64_t share = lv / (uint64_t)world, g = idx / share, loc = idx % share;
+        uint64_t off = 0, s = n_groups / (uint64_t)world;
+        for (int i = 0; i < l; i++) { off += s; s >>= 1; }
+        v = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(arenas.p[g]) + arena_off)[(off + loc) * 8 + (w & 7)];
+    } else {
+        uint64_t off = 0, s = (uint64_t)world;
+        while (s > lv) { off += s; s >>= 1; }
+        v = top[(off + idx) * 8 + (w & 7)];
+    }
+    out[tid] = v;
+}
+
 // One round of Fri::query_phase (src/fri.rs:132-176) for the betas of the transcript: the three points per query
 // (y1, y2 = prev.poly at x1 = g^beta, x2 = -x1; y3 = next.poly at x3 = x1^2: evaluations at domain points are codeword
 // entries, so they are gathered, not re-evaluated), and the two Merkle openings by value search (first leaf equal to y,
@@ -189,10 +215,16 @@ struct QueryLookups {
     std::vector<uint32_t> paths;                     // [2q][path_len][2][8] digest words
     int path_len = 0;
 };
+struct ShardedNodes {  // where a row-sharded tree's digests live (k_gather_paths_sharded); world == 0: not sharded
+    PeerTable arenas{};
+    uint64_t arena_off = 0;
+    int world = 0;
+    const uint32_t* top = nullptr;
+};
 template <class F>
 int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stride, uint64_t nd, const uint32_t* d_prev_nodes,
                       const typename F::T* d_next_cw, uint64_t next_stride, uint64_t next_domain, const uint64_t* betas, uint64_t QF,
-                      QueryLookups<F>* out) {
+                      QueryLookups<F>* out, const ShardedNodes* sharded = nullptr) {
     using T = typename F::T;
     using E = Ext<F>;
     if (!is_pow2(nd) || nd < 2 || next_domain * 2 != nd) return fail(c, MS_ERR_BAD_SHAPE, "FRI query: domains %llu -> %llu", (unsigned long long)nd, (unsigned long long)next_domain);
@@ -247,7 +279,11 @@ int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stri
     MS_LAUNCH_CHECK(c);
     if (path_len) {
         int total = (int)(2 * QF) * path_len * 16;
-        k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
+        if (sharded && sharded->world > 1)
+            k_gather_paths_sharded<<<(total + 255) / 256, 256, 0, c->stream>>>(sharded->arenas, sharded->arena_off, sharded->world, sharded->top, nd / 2,
+                                                                              path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
+        else
+            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
         MS_LAUNCH_CHECK(c);
         MS_TRY(stage_to_host(c, 4 * QF * sizeof(E), d_paths.p, out->paths.size() * 4));
     }

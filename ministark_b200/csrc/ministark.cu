@@ -160,6 +160,12 @@ void ms_ctx_destroy(ms_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->copy_event) cudaEventDestroy(c->copy_event);
     delete c->prover;
+    if (c->comm) {  // not collective here: mappings are dropped without waiting for the peers (use ms_comm_destroy first)
+        if (c->comm->arena) cudaFree(c->comm->arena);
+        c->comm->arena = nullptr;
+        delete c->comm;
+        c->comm = nullptr;
+    }
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -372,6 +378,92 @@ int32_t ms_stark_prove_hooked(ms_ctx* c, const ms_stark_params* p, const void* d
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }
+/* ---- multi-GPU: communicators (csrc/comm.cuh) -------------------------------------------------- */
+int32_t ms_comm_unique_id(uint8_t id128[128]) {
+    NcclApi& api = nccl_api();
+    if (!id128 || !api.load()) return MS_ERR_NCCL;
+    ms_ncclUniqueId id;
+    if (api.GetUniqueId(&id) != 0) return MS_ERR_NCCL;
+    memcpy(id128, id.internal, 128);
+    return MS_OK;
+}
+int32_t ms_comm_init_nccl(ms_ctx* c, const uint8_t id128[128], int32_t rank, int32_t world) {
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(c, MS_ERR_BAD_SHAPE, "ms_comm_init_nccl: rank %d of %d", rank, world);
+    if (c->comm) return fail(c, MS_ERR_UNSUPPORTED, "context already belongs to a communicator");
+    NcclComm* nc = new NcclComm();
+    int rc = nc->init(c, id128, rank, world);
+    if (rc != MS_OK) {
+        delete nc;
+        return rc;
+    }
+    c->comm = nc;
+    return MS_OK;
+}
+int32_t ms_comm_init_local(ms_ctx* const* ctxs, int32_t world) {
+    if (!ctxs || world < 1) return MS_ERR_BAD_SHAPE;
+    for (int g = 0; g < world; g++)
+        if (!ctxs[g] || ctxs[g]->comm) return MS_ERR_UNSUPPORTED;
+    auto grp = std::make_shared<LocalGroup>();
+    grp->world = world;
+    grp->slot.assign(world, nullptr);
+    grp->device.resize(world);
+    for (int g = 0; g < world; g++) grp->device[g] = ctxs[g]->device;
+    for (int g = 0; g < world; g++) {
+        // kernels of rank g read the arenas of the ranks on other devices
+        cudaSetDevice(ctxs[g]->device);
+        for (int h = 0; h < world; h++)
+            if (grp->device[h] != grp->device[g]) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(grp->device[h], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctxs[g], MS_ERR_CUDA, "no peer access %d -> %d: %s", grp->device[g], grp->device[h], cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        LocalComm* lc = new LocalComm();
+        lc->rank = g;
+        lc->world = world;
+        lc->grp = grp;
+        ctxs[g]->comm = lc;
+    }
+    return MS_OK;
+}
+int32_t ms_comm_destroy(ms_ctx* c) {
+    if (!c->comm) return MS_OK;
+    cudaSetDevice(c->device);
+    int rc = c->comm->release(c);
+    delete c->comm;
+    c->comm = nullptr;
+    return rc;
+}
+int32_t ms_comm_info(const ms_ctx* c, int32_t* rank, int32_t* world, const char** backend) {
+    if (rank) *rank = c->comm ? c->comm->rank : 0;
+    if (world) *world = c->comm ? c->comm->world : 1;
+    if (backend) *backend = c->comm ? c->comm->backend() : "none";
+    return MS_OK;
+}
+int32_t ms_set_shard_mask(ms_ctx* c, int32_t mask) {
+    c->shard_mask = mask & MS_SHARD_ALL;
+    return MS_OK;
+}
+int32_t ms_shard_plan(uint64_t cols, uint64_t groups, uint64_t k, int32_t world, int32_t rank, uint64_t* a, uint64_t* b, uint64_t* per_rank,
+                      uint64_t* left) {
+    if (world < 1 || rank < 0 || rank >= world) return MS_ERR_BAD_SHAPE;
+    uint64_t aa, bb, pr = 0, lf = 0;
+    shard_range(cols, world, rank, &aa, &bb);
+    if (a) *a = aa;
+    if (b) *b = bb;
+    const bool ok = subtree_plan(groups, k, world, &pr, &lf);
+    if (per_rank) *per_rank = pr;
+    if (left) *left = lf;
+    return ok ? MS_OK : MS_ERR_BAD_SHAPE;
+}
+int32_t ms_stark_prove_multi(ms_ctx* c, const ms_stark_params* p, const void* d_trace_cm, uint64_t n, uint64_t w, const void* cmat_host,
+                             uint64_t t, uint8_t* proof_out, uint64_t* proof_len, int32_t flags) {
+    if (!c->prover) c->prover = new ms::ProverState();
+    MS_CUDA(c, cudaSetDevice(c->device));
+#define CALL(F) stark_prove<F>(c, c->prover, *p, nullptr, d_trace_cm, n, w, (const F::T*)cmat_host, t, proof_out, proof_len, nullptr, flags)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
 int32_t ms_merkle_subtree(ms_ctx* c, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width, int32_t deg,
                           uint64_t lpn, uint64_t k, uint32_t* d_out, uint64_t* n_out) {
 #define CALL(F) merkle_subtree<F>(c, (const F::T*)d_data, stride, rows, width, deg, lpn, k, d_out, n_out)

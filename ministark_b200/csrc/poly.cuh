@@ -52,7 +52,81 @@ int linear_constraints(Ctx* c, const typename F::T* d_coef, uint64_t stride, uin
     return MS_OK;
 }
 
+// Column-sharded form: trace coefficient column j lives at cols[j] (possibly in a peer GPU's arena, read over
+// NVLink); only the columns a row of the matrix actually uses are touched (zero entries are skipped), so the
+// bidiagonal matrices of the e2e / synthetic AIRs read two columns per constraint.
+template <class F>
+__global__ void k_linear_constraints_gather(const typename F::T* const* __restrict__ cols, uint64_t n, int w,
+                                            const typename F::T* __restrict__ mat, int t, typename F::T* __restrict__ out,
+                                            uint64_t out_stride) {
+    using T = typename F::T;
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    for (int r = 0; r < t; r++) {
+        T acc = 0;
+        for (int j = 0; j < w; j++) {
+            T s = mat[r * w + j];  // warp-uniform
+            if (s == 0) continue;
+            T v = cols[j][m];
+            acc = F::add(acc, s == 1 ? v : F::mul(s, v));
+        }
+        out[(uint64_t)r * out_stride + m] = acc;
+    }
+}
+// rows [t0, t0 + t) of the T x W host matrix applied to the columns in the device pointer table d_cols
+template <class F>
+int linear_constraints_gather(Ctx* c, const typename F::T* const* d_cols, uint64_t n, uint64_t w, const typename F::T* mat_rows_host,
+                              uint64_t t, typename F::T* d_out, uint64_t out_stride) {
+    using T = typename F::T;
+    if (t == 0 || n == 0) return MS_OK;
+    std::vector<T> m(mat_rows_host, mat_rows_host + t * w);
+    for (auto& v : m) v = (T)((uint64_t)v % (uint64_t)F::P);
+    Scratch dm(c);
+    MS_TRY(dm.alloc(t * w * sizeof(T)));
+    MS_TRY(stage_from_host(c, m.data(), ((t * w * sizeof(T) + 3) / 4) * 4, dm.p));
+    k_linear_constraints_gather<F><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_cols, n, (int)w, dm.as<T>(), (int)t, d_out, out_stride);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+
 // ------------------------------------------------------------------------------------------ a6
+// A rank's share of the mix: out[m] = r0a * sum_{i<na} r^i a_i[m] + r0b * sum_{i<nb} r^i b_i[m]  (two runs of
+// consecutive columns with their starting powers r0 = r^(global index of the run's first column)).
+template <class F>
+__global__ void k_mix_parts(const typename F::T* __restrict__ a, uint64_t sa, int na, typename F::T r0a,
+                            const typename F::T* __restrict__ b, uint64_t sb, int nb, typename F::T r0b, uint64_t n,
+                            typename F::T r, typename F::T* __restrict__ out) {
+    using T = typename F::T;
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    T tot = 0;
+    if (na > 0) {
+        T acc = a[(uint64_t)(na - 1) * sa + m];
+        for (int i = na - 2; i >= 0; i--) acc = F::add(F::mul(acc, r), a[(uint64_t)i * sa + m]);
+        tot = F::mul(acc, r0a);
+    }
+    if (nb > 0) {
+        T acc = b[(uint64_t)(nb - 1) * sb + m];
+        for (int i = nb - 2; i >= 0; i--) acc = F::add(F::mul(acc, r), b[(uint64_t)i * sb + m]);
+        tot = F::add(tot, F::mul(acc, r0b));
+    }
+    out[m] = tot;
+}
+constexpr int MS_MAX_RANKS = 16;
+struct PeerTable {
+    const void* p[MS_MAX_RANKS];
+};
+// out[m] = sum_g part_g[m]: the ranks' partial mixes, read from their arenas (exact arithmetic: any order)
+template <class F>
+__global__ void k_sum_peers(PeerTable parts, int world, uint64_t n, typename F::T* __restrict__ out) {
+    using T = typename F::T;
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    T acc = 0;
+    for (int g = 0; g < world; g++) acc = F::add(acc, static_cast<const T*>(parts.p[g])[m]);
+    out[m] = acc;
+}
+
 template <class F>
 __global__ void k_mix(const typename F::T* __restrict__ coef, uint64_t stride, uint64_t n, int cols, typename F::T r,
                       typename F::T* __restrict__ out) {
@@ -112,7 +186,8 @@ __device__ __forceinline__ Ext<F> coef_times(const Ext<F>& c, const Ext<F>& p) {
 template <class F, int CD, int QMAX>
 __global__ void __launch_bounds__(EV_THREADS)
 k_eval_partial(const typename F::T* __restrict__ coef, uint64_t stride, uint64_t off, uint64_t step, uint64_t n,
-               const Ext<F>* __restrict__ tab, int Q, Ext<F>* __restrict__ partial) {
+               const Ext<F>* __restrict__ tab, int Q, Ext<F>* __restrict__ partial, uint64_t poly_off, int shared_planes,
+               uint64_t limit) {
     __shared__ Ext<F> sm[EV_THREADS / 32];
     const uint64_t poly = blockIdx.y, npoly = gridDim.y, nblk = gridDim.x;
     const uint64_t per_q = EV_THREADS + EV_SEG + nblk;
@@ -121,7 +196,10 @@ k_eval_partial(const typename F::T* __restrict__ coef, uint64_t stride, uint64_t
 #pragma unroll
     for (int k = 0; k < EV_SEG; k++) {
         const uint64_t i = i0 + (uint64_t)k * EV_THREADS;
-        cf[k] = i < n ? load_coef<F, CD>(coef, stride, poly, off + i * step) : ext_zero<F>();
+        // polynomial `poly` starts `poly * poly_off` entries further; with shared_planes all polynomials are
+        // subsequences of the same planes (the even / odd halves of one FRI polynomial, src/fri.rs:329-343)
+        const uint64_t idx = off + poly * poly_off + i * step;
+        cf[k] = (i < n && idx < limit) ? load_coef<F, CD>(coef, stride, shared_planes ? 0 : poly, idx) : ext_zero<F>();
     }
     for (int q = 0; q < Q; q++) {
         const Ext<F>* tq = tab + (uint64_t)q * per_q;
@@ -190,7 +268,8 @@ k_eval_final(const Ext<F>* __restrict__ partial, uint64_t nblk, Ext<F>* __restri
 // points; out_host[q*npoly + poly].
 template <class F>
 int eval_points(Ctx* c, const typename F::T* d_coef, uint64_t stride, uint64_t off, uint64_t step, uint64_t n, int coefdeg,
-                uint64_t npoly, const Ext<F>* z_host, int Q, Ext<F>* out_host) {
+                uint64_t npoly, const Ext<F>* z_host, int Q, Ext<F>* out_host, uint64_t poly_off = 0, bool shared_planes = false,
+                uint64_t limit = ~0ULL) {
     if (Q == 0 || npoly == 0) return MS_OK;
     if (n == 0) {
         for (uint64_t i = 0; i < (uint64_t)Q * npoly; i++) out_host[i] = ext_zero<F>();
@@ -210,8 +289,8 @@ int eval_points(Ctx* c, const typename F::T* d_coef, uint64_t stride, uint64_t o
     MS_LAUNCH_CHECK(c);
     dim3 grid((unsigned)nblk, (unsigned)npoly);
     prof_begin(c, "k_eval_partial");
-    if (coefdeg == 1) k_eval_partial<F, 1, 0><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, tab.as<Ext<F>>(), Q, part.as<Ext<F>>());
-    else k_eval_partial<F, F::D, 0><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, tab.as<Ext<F>>(), Q, part.as<Ext<F>>());
+    if (coefdeg == 1) k_eval_partial<F, 1, 0><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, tab.as<Ext<F>>(), Q, part.as<Ext<F>>(), poly_off, shared_planes ? 1 : 0, limit);
+    else k_eval_partial<F, F::D, 0><<<grid, EV_THREADS, 0, c->stream>>>(d_coef, stride, off, step, n, tab.as<Ext<F>>(), Q, part.as<Ext<F>>(), poly_off, shared_planes ? 1 : 0, limit);
     prof_end(c);
     MS_LAUNCH_CHECK(c);
     k_eval_final<F><<<(unsigned)(Q * npoly), EV_THREADS, 0, c->stream>>>(part.as<Ext<F>>(), nblk, dout.as<Ext<F>>());

@@ -3,10 +3,34 @@
 // all bulk data stays on the device.  What crosses the PCIe bus per step is a 32-byte root, a few
 // field elements, and at the very end the proof (whose size is dominated by the per-query FRI
 // quotient polynomials the reference puts in it, fri.rs:167).
+//
+// Multi-GPU: with a communicator bound to the context (comm.cuh; ms_comm_init_nccl /
+// ms_comm_init_local) every rank runs this same function as one replica of the prover and the stages that shard
+// are split over the ranks INSIDE it -- no host callbacks:
+//   trace tree        row ranges -> subtree digests -> all-gather -> join                      (starks.rs:70-72)
+//   iNTT              trace columns [a_g, b_g) per rank, into the rank's peer-readable arena    (air.rs:147-160)
+//   constraints       constraint rows [ta_g, tb_g) per rank; the trace columns a row uses are read from their owners'
+//                     arenas inside the kernel                                                  (air.rs:130-134)
+//   LDE + its tree    each rank extends the columns it owns into its arena; rank h hashes rows [h L/G, (h+1) L/G) with
+//                     one pointer per column into the owners' arenas (NVLink loads under the SHA-256 arithmetic, no
+//                     exchange pass), climbs its subtree; digests all-gathered and joined        (starks.rs:82-94)
+//   mixing            partial sums over the owned columns, summed from the arenas               (starks.rs:108-117)
+//   DEEP openings     owned columns only; Q*C extension elements all-gathered                   (starks.rs:140-151)
+//   FRI round trees   codeword replicated (one polynomial), leaf groups row-sharded for rounds with >= 2^16 leaves:
+//                     subtree per rank kept in its arena, the G roots all-gathered, top log2 G levels replicated;
+//                     authentication paths are gathered from the owners' arenas                 (fri.rs:345-352)
+//   proof download    every rank computes and downloads its share of the quotient polynomials into one shared host
+//                     buffer over its own PCIe link (MS_PROOF_SHARED)                            (fri.rs:167)
+// The transcript, the fold and the deep coefficients run identically on every rank (one polynomial, serial
+// challenges), so all ranks derive the same challenges without a broadcast.  Whenever a split does not exist for a
+// shape (tree not divisible over the ranks, leaf groups spanning several rows ...) that stage falls back to the
+// replicated computation on every rank: the proof bytes never depend on the number of GPUs.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <utility>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "field.cuh"
 #include "fri.cuh"
@@ -21,34 +45,41 @@ struct ProverState {
     std::vector<std::pair<const char*, float>> timings;
 };
 
+// Per-stage device times without stalling the pipeline: event pairs are recorded on the stream and only read
+// back once, after the proof is complete (a cudaEventSynchronize per stage would cost a host round trip each).
 struct StageTimer {
     Ctx* c;
     ProverState* ps;
-    cudaEvent_t ev[2];
-    const char* name = nullptr;
-    StageTimer(Ctx* ctx, ProverState* p) : c(ctx), ps(p) {
-        cudaEventCreate(&ev[0]);
-        cudaEventCreate(&ev[1]);
-    }
+    struct Span { const char* name; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    StageTimer(Ctx* ctx, ProverState* p) : c(ctx), ps(p) {}
     ~StageTimer() {
-        cudaEventDestroy(ev[0]);
-        cudaEventDestroy(ev[1]);
+        for (auto& s : spans) {
+            cudaEventDestroy(s.a);
+            if (s.b) cudaEventDestroy(s.b);
+        }
     }
     void begin(const char* n) {
-        name = n;
-        cudaEventRecord(ev[0], c->stream);
+        Span s{n, nullptr, nullptr};
+        cudaEventCreate(&s.a);
+        cudaEventRecord(s.a, c->stream);
+        spans.push_back(s);
     }
     void end() {
-        cudaEventRecord(ev[1], c->stream);
-        cudaEventSynchronize(ev[1]);
-        float ms_ = 0;
-        cudaEventElapsedTime(&ms_, ev[0], ev[1]);
-        for (auto& e : ps->timings)
-            if (e.first == name) {
-                e.second += ms_;
-                return;
-            }
-        ps->timings.emplace_back(name, ms_);
+        if (spans.empty() || spans.back().b) return;
+        cudaEventCreate(&spans.back().b);
+        cudaEventRecord(spans.back().b, c->stream);
+    }
+    void collect() {  // after the stream has been synchronised
+        for (auto& s : spans) {
+            if (!s.b) continue;
+            float ms_ = 0;
+            if (cudaEventElapsedTime(&ms_, s.a, s.b) != cudaSuccess) continue;
+            bool found = false;
+            for (auto& e : ps->timings)
+                if (e.first == s.name) { e.second += ms_; found = true; break; }
+            if (!found) ps->timings.emplace_back(s.name, ms_);
+        }
     }
 };
 
@@ -68,14 +99,15 @@ struct ProofWriter {
         pos += n;
         return at;
     }
-    bool fits() const { return out && pos <= cap; }
+    bool fits() const { return mute || (out && pos <= cap); }
 };
 
 template <class F>
 struct FriRoundDev {
     typename F::T* poly = nullptr;   // D planes x npad
     typename F::T* cw = nullptr;     // D planes x domain
-    uint32_t* nodes = nullptr;       // (2,2) tree, domain - 1 digests
+    uint32_t* nodes = nullptr;       // (2,2) tree, domain - 1 digests (replicated rounds)
+    ShardedNodes sh;                 // row-sharded rounds: where the digests live
     uint64_t npad = 0, domain = 0, len = 0;
     uint8_t root[32];
 };
@@ -101,10 +133,36 @@ uint64_t proof_size_bound(const ms_stark_params& p, const StarkDerived& d, uint6
     return sz;
 }
 
+constexpr uint64_t FRI_SHARD_MIN_DOMAIN = 1ULL << 16;
+
+// digest words on the device -> root bytes on the host (one small D2H + sync)
+inline int read_root(Ctx* c, const uint32_t* d_digest, uint8_t* root32) {
+    uint32_t w[8];
+    MS_CUDA(c, cudaMemcpyAsync(w, d_digest, 32, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    digest_words_to_bytes(w, root32);
+    return MS_OK;
+}
+
+// A rank's rows of a tree: leaf groups of the aligned row range -> subtree digests -> all-gather -> join.
+// `gather`: d_data is a device table of plane pointers (possibly peer memory), each at the first row of the range.
+template <class F>
+int sharded_tree_root(Ctx* c, Comm* cm, const typename F::T* d_data, uint64_t stride, uint64_t rows, uint64_t width, uint64_t lpn,
+                      uint64_t k, uint64_t left, bool gather, uint8_t* root32) {
+    Scratch mine(c), all(c);
+    MS_TRY(mine.alloc((left ? left : 1) * 32));
+    MS_TRY(all.alloc((size_t)cm->world * left * 32));
+    uint64_t got = 0;
+    MS_TRY(merkle_subtree<F>(c, d_data, stride, rows, width, 1, lpn, k, mine.as<uint32_t>(), &got, gather));
+    if (got != left) return fail(c, MS_ERR_BAD_SHAPE, "subtree left %llu digests, plan says %llu", (unsigned long long)got, (unsigned long long)left);
+    MS_TRY(cm->all_gather(c, mine.p, all.p, left * 32));
+    return merkle_reduce(c, all.as<uint32_t>(), (uint64_t)cm->world * left, k, root32);
+}
+
 template <class F>
 int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* trace_rm_host, const void* d_trace_cm_in,
                 uint64_t n, uint64_t w, const typename F::T* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len,
-                const ms_commit_hooks* hooks = nullptr) {
+                const ms_commit_hooks* hooks = nullptr, int32_t flags = 0) {
     using T = typename F::T;
     using E = Ext<F>;
     constexpr int D = F::D;
@@ -120,10 +178,58 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     const uint64_t lpn = p.trace_columns, kk = p.inner_children ? p.inner_children : 2;
     const uint64_t R = der.rounds, Q = der.constrain_queries, QF = der.fri_queries;
     const uint64_t bound = proof_size_bound<F>(p, der, n, C);
-    if (!proof_out || *proof_len < bound) {
+    // ---- multi-GPU plan: identical on every rank (it only depends on the shape), decided before any collective
+    Comm* cm = (c->comm && c->comm->world > 1 && !hooks) ? c->comm : nullptr;
+    const int G = cm ? cm->world : 1, rank = cm ? cm->rank : 0;
+    if (G > MS_MAX_RANKS) return fail(c, MS_ERR_UNSUPPORTED, "at most %d ranks", MS_MAX_RANKS);
+    const int mask = cm ? c->shard_mask : 0;
+    uint64_t tt_per = 0, tt_left = 0, lt_per = 0, lt_left = 0;
+    const bool sh_trace = (mask & MS_SHARD_TRACE_TREE) && lpn && (n * w) % lpn == 0 && subtree_plan(n * w / lpn, kk, G, &tt_per, &tt_left) &&
+                          (tt_per * lpn) % w == 0;
+    const bool sh_cols = (mask & MS_SHARD_COLUMNS) && lpn == C && subtree_plan(L, kk, G, &lt_per, &lt_left);
+    const bool sh_fri = (mask & MS_SHARD_FRI_TREES) && is_pow2((uint64_t)G);
+    const bool dl_hooks = hooks && hooks->download_world > 1;
+    const bool dl_native = cm && (flags & MS_PROOF_SHARED) && (mask & MS_SHARD_DOWNLOAD);
+    const bool dl_sharded = dl_hooks || dl_native;
+    const uint64_t dl_rank = dl_hooks ? (uint64_t)hooks->download_rank : (dl_native ? (uint64_t)rank : 0);
+    const uint64_t dl_world = dl_hooks ? (uint64_t)hooks->download_world : (dl_native ? (uint64_t)G : 1);
+    // ranks whose proof bytes nobody reads still run every stage that feeds the transcript (lock step) but compute
+    // and download no quotient polynomials
+    const bool replica_only = !dl_sharded && ((hooks && hooks->replica_only) || (cm && rank != 0 && !(flags & MS_PROOF_ALL_RANKS)));
+    if (!(replica_only && cm) && (!proof_out || *proof_len < bound)) {
         *proof_len = bound;
         return fail(c, MS_ERR_BUFFER_TOO_SMALL, "proof buffer needs %llu bytes", (unsigned long long)bound);
     }
+    uint64_t wa = 0, wb = w, ta = 0, tb = t;  // owned trace columns / constraint rows
+    uint64_t max_w = w, max_c = C;
+    size_t off_a = 0, off_b = 0, off_m = 0;  // arena regions: trace coefficients | LDE columns, later FRI nodes | mix partial
+    if (cm) {
+        if (sh_cols) {
+            shard_range(w, G, rank, &wa, &wb);
+            shard_range(t, G, rank, &ta, &tb);
+            max_w = (w + G - 1) / G;
+            max_c = max_w + (t + G - 1) / G;
+        }
+        auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t fri_nodes = 0;
+        if (sh_fri)
+            for (uint64_t dom = L; dom >= FRI_SHARD_MIN_DOMAIN && dom / 2 >= (uint64_t)G; dom >>= 1) fri_nodes += align((dom / G) * 32);
+        const size_t a_bytes = sh_cols ? align(max_w * n * sizeof(T)) : 0;
+        const size_t b_bytes = std::max(sh_cols ? align(max_c * L * sizeof(T)) : (size_t)0, fri_nodes);
+        const size_t m_bytes = sh_cols ? align(n * sizeof(T)) : 0;
+        off_a = 0;
+        off_b = a_bytes;
+        off_m = a_bytes + b_bytes;
+        if (a_bytes + b_bytes + m_bytes) MS_TRY(cm->ensure_arena(c, a_bytes + b_bytes + m_bytes));
+    }
+    auto arena_of = [&](int g, size_t off) -> uint8_t* { return static_cast<uint8_t*>(cm->bases[g]) + off; };
+    auto w_owner = [&](uint64_t col, uint64_t* first) -> int {
+        const int g = shard_owner(w, G, col);
+        uint64_t a, b;
+        shard_range(w, G, g, &a, &b);
+        *first = a;
+        return g;
+    };
     StageTimer tm(c, ps);
     IOPattern io = stark_iopattern(F::BITS, D, R, Q, QF);
     Merlin merlin(io, c->bridge_masks, c->leftover_as_published != 0);
@@ -160,6 +266,9 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     if (hooks && hooks->trace_commit) {
         int rc = hooks->trace_commit(hooks->user, d_trace, n, w, trace_root);
         if (rc != MS_OK) return fail(c, rc, "trace_commit hook failed");
+    } else if (cm && sh_trace) {
+        const uint64_t rows = tt_per * lpn / w;
+        MS_TRY(sharded_tree_root<F>(c, cm, d_trace + (uint64_t)rank * rows, n, rows, w, lpn, kk, tt_left, false, trace_root));
     } else {
         MS_TRY(merkle_commit<F>(c, d_trace, n, n, w, 1, lpn, kk, nullptr, trace_root));
     }
@@ -169,18 +278,81 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     T shift;
     TR(challenge_base(&shift));
     if (shift == 0) return fail(c, MS_ERR_BAD_SHAPE, "random_shift is zero (get_coset unwrap, starks.rs:84-85)");
-    Scratch coeffs(c), lde(c);
-    MS_TRY(coeffs.alloc((C + 1) * n * sizeof(T)));  // C constraint columns + the mixed polynomial
-    tm.begin("intt");
-    MS_TRY(lde_batch<F>(c, d_trace, n, w, ilog2(n), 0, (T)1, true, coeffs.as<T>(), n));  // air.rs:147-160
-    tm.end();
-    tm.begin("constraints");
-    MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
-    tm.end();
+    Scratch coeffs(c), lde(c), ptab(c);
+    T* d_mixed = nullptr;
+    // column-sharded: the owned trace coefficient columns live in the arena (peers read them), the owned constraint
+    // columns and the mixed polynomial in local memory
+    T* my_trace_coef = nullptr;  // [wb - wa][n]
+    T* my_cons_coef = nullptr;   // [tb - ta][n]
+    const uint64_t nw = wb - wa, nt = tb - ta;
+    if (cm && sh_cols) {
+        my_trace_coef = reinterpret_cast<T*>(arena_of(rank, off_a));
+        MS_TRY(coeffs.alloc((nt + 1) * n * sizeof(T)));
+        my_cons_coef = coeffs.as<T>();
+        d_mixed = coeffs.as<T>() + nt * n;
+        tm.begin("intt");
+        MS_TRY(lde_batch<F>(c, d_trace + wa * n, n, nw, ilog2(n), 0, (T)1, true, my_trace_coef, n));  // air.rs:147-160, own columns
+        tm.end();
+        tm.begin("constraints");
+        MS_TRY(cm->barrier(c));  // every rank's trace coefficients are in its arena
+        if (nt) {
+            std::vector<const T*> cols(w);
+            for (uint64_t j = 0; j < w; j++) {
+                uint64_t first;
+                const int g = w_owner(j, &first);
+                cols[j] = reinterpret_cast<const T*>(arena_of(g, off_a)) + (j - first) * n;
+            }
+            MS_TRY(ptab.alloc(w * sizeof(void*)));
+            MS_TRY(stage_from_host(c, cols.data(), w * sizeof(void*), ptab.p));
+            MS_TRY(linear_constraints_gather<F>(c, ptab.as<const T*>(), n, w, cmat_host + ta * w, nt, my_cons_coef, n));  // air.rs:130-134, own rows
+        }
+        tm.end();
+    } else {
+        MS_TRY(coeffs.alloc((C + 1) * n * sizeof(T)));  // C constraint columns + the mixed polynomial
+        d_mixed = coeffs.as<T>() + C * n;
+        tm.begin("intt");
+        MS_TRY(lde_batch<F>(c, d_trace, n, w, ilog2(n), 0, (T)1, true, coeffs.as<T>(), n));  // air.rs:147-160
+        tm.end();
+        tm.begin("constraints");
+        MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
+        tm.end();
+    }
     if (hooks && hooks->lde_commit) {
         tm.begin("lde+commit(hook)");
         int rc = hooks->lde_commit(hooks->user, coeffs.as<T>(), n, C, B, (uint64_t)shift, lde_root);
         if (rc != MS_OK) return fail(c, rc, "lde_commit hook failed");
+        tm.end();
+    } else if (cm && sh_cols) {
+        T* my_lde = reinterpret_cast<T*>(arena_of(rank, off_b));  // [nw + nt][L]: own trace columns, then own constraint columns
+        tm.begin("lde");
+        MS_TRY(lde_batch<F>(c, my_trace_coef, n, nw, ilog2(n), ilog2(B), shift, false, my_lde, L));                 // starks.rs:87-91
+        MS_TRY(lde_batch<F>(c, my_cons_coef, n, nt, ilog2(n), ilog2(B), shift, false, my_lde + nw * L, L));
+        tm.end();
+        tm.begin("lde_commit");
+        MS_TRY(cm->barrier(c));  // every rank's columns are complete before anyone reads them
+        const uint64_t rows = lt_per;  // lpn == C: one row per leaf group
+        std::vector<const T*> planes(C);
+        for (uint64_t col = 0; col < C; col++) {
+            int g;
+            uint64_t local;
+            if (col < w) {
+                uint64_t first;
+                g = w_owner(col, &first);
+                local = col - first;
+            } else {
+                g = shard_owner(t, G, col - w);
+                uint64_t a, b, a2, b2;
+                shard_range(t, G, g, &a, &b);
+                shard_range(w, G, g, &a2, &b2);
+                local = (b2 - a2) + (col - w - a);
+            }
+            planes[col] = reinterpret_cast<const T*>(arena_of(g, off_b)) + local * L + (uint64_t)rank * rows;
+        }
+        Scratch ltab(c);
+        MS_TRY(ltab.alloc(C * sizeof(void*)));
+        MS_TRY(stage_from_host(c, planes.data(), C * sizeof(void*), ltab.p));
+        // the all-gather inside also tells every rank that its columns have been read (the region is reused below)
+        MS_TRY(sharded_tree_root<F>(c, cm, ltab.as<T>(), 0, rows, C, lpn, kk, lt_left, true, lde_root));  // starks.rs:92-94
         tm.end();
     } else {
         MS_TRY(lde.alloc(C * L * sizeof(T)));
@@ -197,9 +369,20 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     // ---- 1.3 mixing                                                                  starks.rs:108-119
     T r;
     TR(challenge_base(&r));
-    T* d_mixed = coeffs.as<T>() + C * n;
     tm.begin("mix");
-    MS_TRY(mix<F>(c, coeffs.as<T>(), n, n, C, r, d_mixed));
+    if (cm && sh_cols) {
+        T* part = reinterpret_cast<T*>(arena_of(rank, off_m));
+        k_mix_parts<F><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(my_trace_coef, n, (int)nw, fpow<F>(r, wa), my_cons_coef, n, (int)nt,
+                                                                          fpow<F>(r, w + ta), n, r, part);
+        MS_LAUNCH_CHECK(c);
+        MS_TRY(cm->barrier(c));
+        PeerTable pt{};
+        for (int g = 0; g < G; g++) pt.p[g] = arena_of(g, off_m);
+        k_sum_peers<F><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pt, G, n, d_mixed);
+        MS_LAUNCH_CHECK(c);
+    } else {
+        MS_TRY(mix<F>(c, coeffs.as<T>(), n, n, C, r, d_mixed));
+    }
     tm.end();
     // divide_by_vanishing_poly yields (quotient, remainder); the reference asserts quotient == 0,
     // which holds for any polynomial with <= N coefficients, and carries the remainder (= mixed) on.
@@ -208,35 +391,71 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     TR(challenge_exts(zq.data(), Q));  // merlin.fill_challenge_scalars(&mut queries), starks.rs:124-125
     std::vector<E> opens(Q * (C + 1));
     tm.begin("deep_open");
-    MS_TRY(eval_points<F>(c, coeffs.as<T>(), n, 0, 1, n, 1, C + 1, zq.data(), (int)Q, opens.data()));
+    if (cm && sh_cols) {
+        // own columns, then every rank's results gathered: rank g contributes [Q][max_c] slots (its trace columns, then
+        // its constraint columns); the mixed polynomial is evaluated by everyone (one polynomial)
+        std::vector<E> mine(Q * max_c, ext_zero<F>()), tmp(Q * std::max<uint64_t>(std::max(nw, nt), 1)), vq(Q);
+        if (nw) {
+            MS_TRY(eval_points<F>(c, my_trace_coef, n, 0, 1, n, 1, nw, zq.data(), (int)Q, tmp.data()));
+            for (uint64_t q = 0; q < Q; q++)
+                for (uint64_t j = 0; j < nw; j++) mine[q * max_c + j] = tmp[q * nw + j];
+        }
+        if (nt) {
+            MS_TRY(eval_points<F>(c, my_cons_coef, n, 0, 1, n, 1, nt, zq.data(), (int)Q, tmp.data()));
+            for (uint64_t q = 0; q < Q; q++)
+                for (uint64_t j = 0; j < nt; j++) mine[q * max_c + nw + j] = tmp[q * nt + j];
+        }
+        MS_TRY(eval_points<F>(c, d_mixed, n, 0, 1, n, 1, 1, zq.data(), (int)Q, vq.data()));
+        Scratch ds(c), dr(c);
+        const size_t blk = Q * max_c * sizeof(E);
+        MS_TRY(ds.alloc(blk));
+        MS_TRY(dr.alloc(blk * G));
+        MS_CUDA(c, cudaMemcpyAsync(ds.p, mine.data(), blk, cudaMemcpyHostToDevice, c->stream));
+        MS_TRY(cm->all_gather(c, ds.p, dr.p, blk));
+        std::vector<E> all(Q * max_c * G);
+        MS_CUDA(c, cudaMemcpyAsync(all.data(), dr.p, blk * G, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int g = 0; g < G; g++) {
+            uint64_t a, b, a2, b2;
+            shard_range(w, G, g, &a, &b);
+            shard_range(t, G, g, &a2, &b2);
+            for (uint64_t q = 0; q < Q; q++) {
+                for (uint64_t j = a; j < b; j++) opens[q * (C + 1) + j] = all[((uint64_t)g * Q + q) * max_c + (j - a)];
+                for (uint64_t j = a2; j < b2; j++) opens[q * (C + 1) + w + j] = all[((uint64_t)g * Q + q) * max_c + (b - a) + (j - a2)];
+            }
+        }
+        for (uint64_t q = 0; q < Q; q++) opens[q * (C + 1) + C] = vq[q];
+    } else {
+        MS_TRY(eval_points<F>(c, coeffs.as<T>(), n, 0, 1, n, 1, C + 1, zq.data(), (int)Q, opens.data()));
+    }
     tm.end();
     // ---- 3. FRI commit phase                                                        fri.rs:64-113
     tm.begin("fri_commit_phase");
     std::vector<FriRoundDev<F>> rounds(R);
     std::vector<Scratch> keep;
-    keep.reserve(4 * R + 8);
+    keep.reserve(5 * R + 8);
     auto dev_alloc = [&](size_t bytes, void** out) -> int {
         keep.emplace_back(c);
         MS_TRY(keep.back().alloc(bytes));
         *out = keep.back().p;
         return MS_OK;
     };
-    Scratch d_len(c);
-    MS_TRY(d_len.alloc(8));
-    auto poly_len = [&](const T* planes, uint64_t stride, int nplanes, uint64_t npad, uint64_t* out) -> int {
-        MS_CUDA(c, cudaMemsetAsync(d_len.p, 0, 8, c->stream));
-        k_poly_len<F><<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(planes, stride, nplanes, npad, d_len.as<unsigned long long>());
+    // coefficient counts of all rounds: computed on the device as the rounds are produced, read back once (the
+    // commit phase itself only needs the padded sizes; `len` matters for the quotient lengths of the query phase)
+    Scratch d_lens(c);
+    MS_TRY(d_lens.alloc(8 * (R + 1)));
+    MS_CUDA(c, cudaMemsetAsync(d_lens.p, 0, 8 * (R + 1), c->stream));
+    auto poly_len_async = [&](const T* planes, uint64_t stride, int nplanes, uint64_t npad, uint64_t slot) -> int {
+        k_poly_len<F><<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(planes, stride, nplanes, npad, d_lens.as<unsigned long long>() + slot);
         MS_LAUNCH_CHECK(c);
-        unsigned long long v = 0;
-        MS_CUDA(c, cudaMemcpyAsync(&v, d_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
-        MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        *out = v;
         return MS_OK;
     };
     {
         // round 0: the mixed polynomial lifted to the extension (field.rs:23-32): upper planes zero.
-        uint64_t len0 = 0;
-        MS_TRY(poly_len(d_mixed, n, 1, n, &len0));
+        MS_TRY(poly_len_async(d_mixed, n, 1, n, 0));
+        unsigned long long len0 = 0;
+        MS_CUDA(c, cudaMemcpyAsync(&len0, d_lens.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
         uint64_t deg = len0 ? len0 - 1 : 0;  // ark: degree() of the zero polynomial is 0
         uint64_t npad = 1;
         while (npad < deg + 1) npad <<= 1;  // Radix2EvaluationDomain::new((deg+1)*B) rounds up (fri.rs:74,315)
@@ -248,6 +467,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         MS_CUDA(c, cudaMemsetAsync(r0.poly, 0, D * npad * sizeof(T), c->stream));
         MS_CUDA(c, cudaMemcpyAsync(r0.poly, d_mixed, npad * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
     }
+    size_t fri_arena_used = 0;
     for (uint64_t i = 0; i < R; i++) {
         FriRoundDev<F>& cur = rounds[i];
         if (i > 0) {
@@ -265,12 +485,40 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             MS_TRY(dev_alloc(D * cur.npad * sizeof(T), (void**)&cur.poly));
             MS_CUDA(c, cudaMemsetAsync(cur.poly, 0, D * cur.npad * sizeof(T), c->stream));
             MS_TRY(fri_fold<F>(c, prev.poly, prev.npad, prev.npad, z.c, alpha.c, deep[0].c, cur.poly, cur.npad));  // fri.rs:97-101
-            MS_TRY(poly_len(cur.poly, cur.npad, D, cur.npad, &cur.len));
+            MS_TRY(poly_len_async(cur.poly, cur.npad, D, cur.npad, i));
         }
         MS_TRY(dev_alloc(D * cur.domain * sizeof(T), (void**)&cur.cw));
-        MS_TRY(dev_alloc((cur.domain - 1) * 32, (void**)&cur.nodes));
-        MS_TRY(fri_commit<F>(c, cur.poly, cur.npad, cur.domain, cur.domain / cur.npad, cur.cw, cur.domain, cur.nodes, cur.root));  // fri.rs:345-352
+        const uint64_t groups = cur.domain / 2;
+        if (cm && sh_fri && cur.domain >= FRI_SHARD_MIN_DOMAIN && groups >= (uint64_t)G) {
+            // codeword replicated, tree row-sharded (fri.rs:345-352): this rank's leaf groups -> its subtree (kept in the
+            // arena for the authentication paths) -> the G subtree roots all-gathered -> the top levels on every rank
+            const uint64_t per = groups / G, npadc = cur.npad;
+            MS_TRY(lde_batch<F>(c, cur.poly, npadc, D, ilog2(npadc), ilog2(cur.domain / npadc), (T)1, false, cur.cw, cur.domain));
+            uint32_t* mine = reinterpret_cast<uint32_t*>(arena_of(rank, off_b + fri_arena_used));
+            MS_TRY(merkle_leaf_level<F>(c, cur.cw + (uint64_t)rank * 2 * per, cur.domain, 1, D, 2, per, mine));
+            uint64_t top_at = 0;
+            MS_TRY(merkle_climb(c, mine, per, 2, 1, &top_at));
+            uint32_t* top = nullptr;
+            MS_TRY(dev_alloc((size_t)(2 * G) * 32, (void**)&top));
+            MS_TRY(cm->all_gather(c, mine + top_at * 8, top, 32));
+            MS_TRY(merkle_upper_levels(c, top, (uint64_t)G, 2));
+            MS_TRY(read_root(c, top + (size_t)(2 * G - 2) * 8, cur.root));
+            cur.sh.world = G;
+            cur.sh.arena_off = off_b + fri_arena_used;
+            cur.sh.top = top;
+            for (int g = 0; g < G; g++) cur.sh.arenas.p[g] = cm->bases[g];
+            fri_arena_used += ((2 * per) * 32 + 255) & ~(size_t)255;
+        } else {
+            MS_TRY(dev_alloc((cur.domain - 1) * 32, (void**)&cur.nodes));
+            MS_TRY(fri_commit<F>(c, cur.poly, cur.npad, cur.domain, cur.domain / cur.npad, cur.cw, cur.domain, cur.nodes, cur.root));  // fri.rs:345-352
+        }
         if (i > 0) TR(merlin.add_bytes(cur.root, 32));                                  // fri.rs:107-108 (round 0 is not absorbed)
+    }
+    {
+        std::vector<unsigned long long> lens(R);
+        MS_CUDA(c, cudaMemcpyAsync(lens.data(), d_lens.p, 8 * R, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (uint64_t i = 1; i < R; i++) rounds[i].len = lens[i];
     }
     tm.end();
     // ---- FRI query phase                                                            fri.rs:115-189
@@ -281,8 +529,6 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     for (uint64_t k = 0; k < QF; k++) memcpy(&betas[k], &braw[8 * k], 8);               // usize::from_le_bytes
     // ---- serialise the fixed part (field order of starks.rs:21-28)
     // sharded download: every rank computes the same offsets, rank 0 alone writes the fixed part
-    const bool dl_sharded = hooks && hooks->download_world > 1;
-    const uint64_t dl_rank = dl_sharded ? (uint64_t)hooks->download_rank : 0, dl_world = dl_sharded ? (uint64_t)hooks->download_world : 1;
     uint64_t copy_seq = 0;
     // Which rank downloads (and therefore computes) the seq-th quotient polynomial.  From 4 ranks on, rank 0 takes
     // none: it is the only one that runs the look-ups and writes the fixed part, which is then the critical path.
@@ -290,8 +536,8 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         if (dl_world >= 4) return dl_rank != 0 && seq % (dl_world - 1) + 1 == dl_rank;
         return seq % dl_world == dl_rank;
     };
-    ProofWriter pw(proof_out, *proof_len);
-    pw.mute = dl_sharded && dl_rank != 0;
+    ProofWriter pw(proof_out, proof_out ? *proof_len : 0);
+    pw.mute = (dl_sharded && dl_rank != 0) || (replica_only && (!proof_out || *proof_len < bound));
     pw.bytes("MSTARKP1", 8);
     pw.u32((uint32_t)F::ID);
     pw.u32((uint32_t)D);
@@ -332,7 +578,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         const bool lookups = !pw.mute;
         QueryLookups<F> lk;
         if (lookups) {
-            MS_TRY(fri_query_lookups<F>(c, prev.cw, prev.domain, nd, prev.nodes, nxt.cw, nxt.domain, nxt.domain, betas.data(), QF, &lk));
+            MS_TRY(fri_query_lookups<F>(c, prev.cw, prev.domain, nd, prev.nodes, nxt.cw, nxt.domain, nxt.domain, betas.data(), QF, &lk, &prev.sh));
             q_host[0] += now_ms() - t_q; t_q = now_ms();
         } else {
             const T g_prev = root_of_unity<F>(ilog2(nd));
@@ -354,7 +600,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         if (nq) {
             std::vector<T> s2_own;
             for (uint64_t k = 0; k < QF; k++)
-                if (owns(copy_seq + k) && !(hooks && hooks->replica_only && !dl_sharded)) {
+                if (owns(copy_seq + k) && !replica_only) {
                     slot[k] = (int)s2_own.size();
                     s2_own.push_back(s2[k]);
                 }
@@ -436,8 +682,11 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         *proof_len = pw.pos;
         return fail(c, MS_ERR_BUFFER_TOO_SMALL, "proof buffer needs %llu bytes", (unsigned long long)pw.pos);
     }
-    MS_CUDA(c, cudaStreamSynchronize(c->stream));
     tm.end();
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    // every rank's share of a shared proof buffer has landed, and nobody still reads this rank's arena
+    if (cm) MS_TRY(cm->host_barrier(c));
+    tm.collect();
     *proof_len = pw.pos;
 #undef TR
     return MS_OK;
