@@ -2,25 +2,32 @@
 """bench.py -- headline benchmark of the mini-stark prover hot path on B200.
 
 Metric (BASELINE.json): "prove ms & LDE Melem/s, Goldilocks 2^22 rows x 32 cols, 1/2/4/8 B200".
-  value   = LDE Melem/s: L*C output elements / device time of the batched coset LDE (coefficients
-            resident in HBM -> evaluations resident in HBM, coset scaling included), blowup 4.
-  e2e     = the same metric through the C-ABI host-buffer call ms_coset_lde_host (pinned host
-            coefficients in, row-major host evaluations out; H2D + D2H inside the timed region).
-  prove   = extra key: full Stark::prove of the synthetic AIR on the same shape (W=16, T=16), device
-            resident trace -> proof bytes on the host, and host trace -> proof bytes.
-A "step" is one LDE of the whole 2^22 x 32 batch.  With --gpus N every rank owns an independent
-2^22 x 32 column shard (columns are independent: SURVEY.md 8e), no data-path collective: weak scaling.
+  value     = LDE Melem/s of ONE 2^22 x 32 problem: L*C output elements / device time of the batched coset LDE
+              (coefficients resident in HBM -> evaluations resident in HBM, coset scaling included), blowup 4.
+              With --gpus N the 32 columns are sharded over the ranks (columns are independent; no data-path
+              collective): STRONG scaling, time = max over ranks.  `lde_weak` keeps the old N-independent-replicas number.
+  prove_ms  = full Stark::prove of the synthetic AIR on the same shape (W = 16, T = 16), device-resident trace -> proof
+              bytes on the host; at N > 1 one proof strong-scaled through the library's own multi-GPU path
+              (ms_stark_prove_multi over NCCL + CUDA IPC, csrc/comm.cuh).  The proof's sha256 is asserted against the digest
+              the C oracle produced for this shape (tests/golden/scale_proofs.json).
+  e2e       = the LDE metric through the C-ABI host-buffer call ms_coset_lde_host (pinned host coefficients in, row-major
+              host evaluations out; H2D + D2H inside the timed region).
+  roofline  = LDE: algorithmic bytes / time against the measured HBM peak, plus `alu`: thread instructions per second
+              against the INT32 issue ceiling 148 SM x 64 lanes x f (the kernel is integer-issue bound).
+  cpu_baseline / --impl reference = the C restatement of the reference (oracle/, "port": the reference is Rust and cannot
+              be built here) for the LDE and for the whole prove.
+A "step" is one LDE of the whole 2^22 x 32 batch.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -28,12 +35,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GL = 0
-P_GL = 2**64 - 2**32 + 1
-SHIFT = 0x123456789ABCDEF % P_GL  # fixed coset offset for the stage benchmark (injected challenge)
-# measured under ncu --set full for the headline shape (profiles/r01_e_ncu_ntt.txt):
-# pass 1 1.211 + 4.257 GB, pass 2 4.297 + 4.268 GB (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_TRAFFIC_BYTES = 14_033_000_000
+GL, BB = 0, 1
+P = {GL: 2**64 - 2**32 + 1, BB: 2013265921}
+SHIFT = 0x123456789ABCDEF  # fixed coset offset for the stage benchmark (injected challenge)
+SEED = 0x5EED000000000000
+N_SM, INT32_LANES_PER_SM = 148, 64  # B300_MICROARCH.md: ALU and FMA pipes, one warp instruction per 2 clocks per scheduler each
 
 
 def parse():
@@ -48,6 +54,7 @@ def parse():
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BabyBear line and the config 3a / 5a proofs")
     ap.add_argument("--security-bits", type=int, default=100)
     return ap.parse_args()
 
@@ -58,6 +65,30 @@ def peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def golden_digest(name):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "scale_proofs.json")) as fh:
+            return json.load(fh).get(name)
+    except OSError:
+        return None
+
+
+def ncu_summary(kind):
+    """per-launch counters of the LDE kernels from the committed ncu capture (profiles/r02_ncu_<kind>.json, written by
+    profiles/ncu_extract.py from the .ncu-rep), valid only for the kernel source they were captured from"""
+    path = os.path.join(ROOT, "profiles", f"r02_ncu_{kind}.json")
+    try:
+        with open(path) as fh:
+            s = json.load(fh)
+    except OSError:
+        return None
+    src = os.path.join(ROOT, "ministark_b200", "csrc", "ntt.cuh")
+    with open(src, "rb") as fh:
+        if hashlib.sha256(fh.read()).hexdigest() != s.get("ntt_cuh_sha256"):
+            return None  # the kernel changed since the capture: no stale numbers
+    return s
 
 
 class ClockSampler:
@@ -110,24 +141,31 @@ class ClockSampler:
 
 
 def workload_name(args):
-    return (f"goldilocks coset-LDE 2^{args.log_rows} rows x {args.cols} cols blowup {args.blowup} per GPU "
+    return (f"goldilocks coset-LDE 2^{args.log_rows} rows x {args.cols} cols blowup {args.blowup}, one problem "
             f"(BASELINE headline shape; coefficients -> evaluations on shift*<w_L>)")
 
 
-def synth_coeffs(n, cols, seed):
-    """poly-major [cols, n] canonical Goldilocks coefficients (NTT sweep treats all C
-    columns as coefficient vectors)."""
-    from tests.synth import synth_trace
+def synth_coeffs(field, n, cols, seed):
+    """poly-major [cols, n] canonical coefficients (the NTT sweep treats all C columns as coefficient vectors)"""
+    from ministark_b200.synth import synth_trace
 
-    return np.ascontiguousarray(synth_trace(GL, n, cols, seed=seed).T)
+    return np.ascontiguousarray(synth_trace(field, n, cols, seed=seed).T)
+
+
+def headline_air(args):
+    """the synthetic AIR of the prove metric: W = C/2 trace columns, T = W bidiagonal constraints"""
+    from ministark_b200.synth import synth_linear_matrix
+
+    n, W = 1 << args.log_rows, args.cols // 2
+    return n, W, synth_linear_matrix(GL, n, W), SEED + 1
 
 
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """The reference's own CPU algorithm for the path.  The reference is Rust and cannot be built in
-    this image (no cargo/rustc), so this times the oracle port (oracle/liboracle.so: per-column
-    radix-2 coset transforms + stride-C scatter, starks.rs:87-91) with every host thread on a bounded
-    sample of the workload's columns."""
+    """The reference's own CPU algorithm for the path.  The reference is Rust and cannot be built in this image (no
+    cargo/rustc), so this times the C restatement (oracle/liboracle.so) with every host thread: the LDE loop of
+    starks.rs:87-91 on a bounded sample of the workload's columns per step (the metric line), and ONE whole Stark::prove
+    of the headline shape (starks.rs:59-169 + fri.rs:53-189; extra key `prove`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -137,19 +175,40 @@ def run_reference(args):
     n, B = 1 << args.log_rows, args.blowup
     threads = os.cpu_count() or 1
     cols = min(args.cols, max(1, threads))
-    coeffs = synth_coeffs(n, cols, 1)
+    coeffs = synth_coeffs(GL, n, cols, 1)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        O.coset_lde(GL, coeffs, n * B, SHIFT, threads=threads)
+        O.coset_lde(GL, coeffs, n * B, SHIFT % P[GL], threads=threads)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
     t = float(np.mean(times))
     val = n * B * cols / t / 1e6
+    prove = None
+    if not args.no_prove:
+        from ministark_b200.synth import synth_trace
+
+        n, W, m, seed = headline_air(args)
+        tr = synth_trace(GL, n, W, seed=seed)
+        params = O.StarkParams(args.security_bits, B, n - 1, args.cols, 2)
+        import ctypes as Cc
+
+        bound = O.lib().or_stark_proof_bound(GL, Cc.byref(params), n, args.cols)
+        buf = np.empty(bound, dtype=np.uint8)
+        t0 = time.perf_counter()
+        plen, stages = O.stark_prove_into(GL, params, tr, m, buf, threads=threads)
+        wall = time.perf_counter() - t0
+        g = golden_digest(f"headline_gl_2^{args.log_rows}x{args.cols}_b{B}") if args.security_bits == 100 else None
+        digest = hashlib.sha256(buf[:plen].tobytes()).hexdigest()
+        prove = {"prove_ms": wall * 1e3, "threads": threads, "proof_bytes": int(plen), "proof_sha256": digest,
+                 "matches_committed_digest": (digest == g["proof_sha256"]) if g else None,
+                 "stages_ms": {k: round(v, 1) for k, v in stages.items()},
+                 "what": "C restatement of Stark::prove (oracle/prover.inc) on the headline shape, all host threads (the reference "
+                         "itself is single-threaded)"}
     line = {
         "impl": "reference", "metric": "lde_melem_per_s", "value": val, "unit": "Melem/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": f"{cols} of {args.cols} columns per step"},
         "cpu_baseline": {"value": val, "unit": "Melem/s", "cores": min(threads, cols), "kind": "port",
@@ -157,6 +216,9 @@ def run_reference(args):
                                    "(reference is Rust; no toolchain in the image)"},
         "e2e": {"value": val, "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if prove:
+        line["prove_ms"] = prove["prove_ms"]
+        line["prove"] = prove
     print(json.dumps(line))
 
 
@@ -175,24 +237,52 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     from ministark_b200 import Context
     from ministark_b200._lib import StarkParams
+    from ministark_b200.sharded import column_ranges
 
     dev = local_rank
     torch.cuda.set_device(dev)
     ctx = Context(GL, dev)
+    if world > 1:
+        # the library's own communicator: the 128-byte id travels over torch.distributed (plumbing), everything
+        # else -- barriers, digest all-gathers, IPC arenas -- is inside libministark.so
+        uid = [Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_nccl(uid[0], rank, world)
     n, C, B = 1 << args.log_rows, args.cols, args.blowup
     L = n * B
     peak, peak_src = peaks()
+    shift = SHIFT % P[GL]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident LDE ------------------------------------------------------------------
-    coeffs = ctx.to_device(synth_coeffs(n, C, 1 + rank))
-    out = ctx.empty(C, L)
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{dev}")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_lde(c, coeffs, out, blowup, steps, warmup):
+        for _ in range(warmup):
+            c.coset_lde(coeffs, blowup, shift, out=out)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            c.coset_lde(coeffs, blowup, shift, out=out)  # inputs + outputs exceed L2 at the headline shape: no flush needed
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / steps
+
+    # ---- device-resident LDE: ONE problem, this rank's column share --------------------------------------
+    a, b = column_ranges(C, world)[rank]
+    all_coeffs = ctx.trace_synth(n, C, seed=1)  # [C, n] on the device (same values as synth_coeffs(GL, n, C, 1))
+    coeffs = all_coeffs[a:b]
+    out = ctx.empty(max(b - a, 1), L)
     for _ in range(args.warmup):
-        ctx.coset_lde(coeffs, B, SHIFT, out=out)
+        ctx.coset_lde(coeffs, B, shift, out=out)
     barrier()
     sampler = ClockSampler(dev)
     if rank == 0:
@@ -204,87 +294,79 @@ def run_ours(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        ctx.coset_lde(coeffs, B, SHIFT, out=out)  # inputs (1 GiB) + outputs (4 GiB) exceed L2: no flush needed
+        ctx.coset_lde(coeffs, B, shift, out=out)
     ev1.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     launches = ctx.launch_count() - launches0
     kern = ctx.profile_collect()
     ctx.set_profiling(False)
-    # the sampler keeps running through the e2e section below (GPU busy throughout), so that the median is taken
-    # over a dozen samples under load instead of the one or two that fit the 50 ms LDE region
-    t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{dev}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = world * L * C / (ms_step * 1e-3) / 1e6
+    value = L * C / (ms_step * 1e-3) / 1e6
+    lde_weak = None
+    if world > 1:  # the old number: every rank extends all 32 columns (N independent replicas)
+        out_w = ctx.empty(C, L)
+        ms_w = time_lde(ctx, all_coeffs, out_w, B, args.steps, 2)
+        lde_weak = {"value": world * L * C / (ms_w * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": ms_w,
+                    "what": f"{world} independent 2^{args.log_rows} x {C} replicas (weak scaling, no sharding)"}
+        del out_w
 
-    # ---- e2e: host buffers through ms_coset_lde_host -------------------------------------------
+    # ---- e2e: host buffers through ms_coset_lde_host (this rank's column share) -------------------------
     e2e = None
     if not args.no_e2e:
-        h_in = torch.from_numpy(synth_coeffs(n, C, 1 + rank).view(np.int64)).pin_memory()
-        h_out = torch.empty((L, C), dtype=torch.int64).pin_memory()
+        nc = max(b - a, 1)
+        h_in = torch.from_numpy(synth_coeffs(GL, n, C, 1)[a:a + nc].view(np.int64)).pin_memory()
+        h_out = torch.empty((L, nc), dtype=torch.int64).pin_memory()
         in_np, out_np = h_in.numpy().view(np.uint64), h_out.numpy().view(np.uint64)
         for _ in range(2):
-            ctx.coset_lde_host(in_np, B, SHIFT, out=out_np)
+            ctx.coset_lde_host(in_np, B, shift, out=out_np)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.coset_lde_host(in_np, B, SHIFT, out=out_np)  # synchronous: returns when the result is on the host
+            ctx.coset_lde_host(in_np, B, shift, out=out_np)  # synchronous: returns when the result is on the host
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item()) / args.steps
-        # spot check: the host result equals the device result
-        assert (out_np[:4] == ctx.to_host(out[:, :4]).T).all() or rank != 0
-        e2e = {"value": world * L * C / e2e_s / 1e6, "unit": "Melem/s", "ms_per_step": e2e_s * 1e3,
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+        assert (out_np[:4] == ctx.to_host(out[:, :4]).T).all(), "host-buffer LDE differs from the device-resident one"
+        e2e = {"value": L * C / e2e_s / 1e6, "unit": "Melem/s", "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": int(n * C * 8), "d2h_bytes_per_step": int(L * C * 8),
-               "call": "ms_coset_lde_host (pinned host buffers, row-major evaluations out)"}
+               "call": "ms_coset_lde_host (pinned host buffers, row-major evaluations out); at N > 1 every rank moves its column share"}
         del h_in, h_out
 
     clocks = sampler.stop() if rank == 0 else None  # window = the LDE and e2e regions (GPU busy throughout)
-    # ---- full prove on the same shape -------------------------------------------------------------
-    # N = 1: the plain prover.  N > 1: one replica per GPU with the trace tree and the LDE + its tree
-    # sharded (ministark_b200/sharded.py): strong scaling of one proof, max over ranks.
+
+    # ---- full prove on the same shape -----------------------------------------------------------------------
     prove = None
     if not args.no_prove:
-        from ministark_b200.sharded import SharedProofBuffer, stark_prove_sharded
-        from tests.synth import synth_linear_matrix, synth_trace
+        from ministark_b200.sharded import SharedProofBuffer
 
-        W = C // 2
-        steps = n - 1
-        trace_rm = synth_trace(GL, n, W, seed=0x5EED000000000000 + 1)
-        m = synth_linear_matrix(GL, n, W)
-        params = StarkParams(args.security_bits, B, steps, C, 2)
+        n_, W, m, seed = headline_air(args)
+        params = StarkParams(args.security_bits, B, n - 1, C, 2)
         bound = int(ctx.lib.ms_stark_proof_bound(GL, params, n, C))
         shared = None
-        if world > 1:  # one shared host buffer: every rank downloads 1/world of the quotient polynomials
+        if world > 1:  # one shared host buffer: every rank downloads its share of the quotient polynomials
             shared = SharedProofBuffer(ctx, bound, dist)
             proof_buf = shared.array
         else:
             proof_buf = torch.empty(bound, dtype=torch.uint8).pin_memory().numpy()
-        trace_cm = ctx.to_device(np.ascontiguousarray(trace_rm.T))
+        trace_cm = ctx.trace_synth(n, W, seed=seed)  # generated on the device (ms_trace_synth): no upload
         torch.cuda.synchronize()
         ms_dev, ms_host, plen, stages = [], [], 0, None
-        for i in range(3):
+        for i in range(4):
             barrier()
             t0 = time.perf_counter()
             if world > 1:
-                plen = stark_prove_sharded(ctx, params, trace_cm, m, shared, dist)
+                plen = ctx.stark_prove_multi(params, trace_cm, m, proof_buf, shared=True)
             else:
                 plen = ctx.stark_prove_device(params, trace_cm, m, proof_buf)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
-            if dist is not None:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = max_over_ranks(time.perf_counter() - t0)
             if i > 0:
-                ms_dev.append(float(tt.item()) * 1e3)
+                ms_dev.append(dt * 1e3)
                 stages = ctx.last_timings()
+        digest = hashlib.sha256(proof_buf[:plen].tobytes()).hexdigest() if rank == 0 else None
         if world == 1:
-            h_trace = torch.from_numpy(trace_rm.view(np.int64)).pin_memory().numpy().view(np.uint64)
+            from ministark_b200.synth import synth_trace
+
+            h_trace = torch.from_numpy(synth_trace(GL, n, W, seed=seed).view(np.int64)).pin_memory().numpy().view(np.uint64)
             import ctypes as Cc
 
             for i in range(4):
@@ -297,67 +379,174 @@ def run_ours(args):
                 ctx._check(rc)
                 if i > 0:
                     ms_host.append(dt * 1e3)
-        import hashlib
-
-        prove = {"prove_ms": float(np.mean(ms_dev)), "prove_e2e_ms": float(np.median(ms_host)) if ms_host else None,
+            assert hashlib.sha256(proof_buf[: cap.value].tobytes()).hexdigest() == digest, "host-trace proof differs from the device-trace proof"
+        g = golden_digest(f"headline_gl_2^{args.log_rows}x{C}_b{B}") if args.security_bits == 100 else None
+        if rank == 0 and g is not None:
+            assert plen == g["proof_len"] and digest == g["proof_sha256"], \
+                f"proof differs from the C oracle's (tests/golden/scale_proofs.json): {digest} vs {g['proof_sha256']}"
+        prove = {"prove_ms": float(np.mean(ms_dev)), "prove_samples_ms": [round(v, 2) for v in ms_dev],
+                 "prove_e2e_ms": float(np.median(ms_host)) if ms_host else None,
                  "prove_e2e_samples_ms": [round(v, 2) for v in ms_host],
-                 "proof_bytes": plen, "proof_sha256": hashlib.sha256(proof_buf[:plen].tobytes()).hexdigest(),
-                 "scaling": "strong (one proof; commitments and the proof download sharded over the ranks, FRI replicated)" if world > 1 else "single GPU",
+                 "proof_bytes": plen, "proof_sha256": digest, "matches_oracle_digest": (g is not None) if rank == 0 else None,
+                 "oracle_digest_source": "tests/golden/scale_proofs.json (C restatement of Stark::prove, tests/golden/make_golden.py)",
+                 "scaling": ("strong: one proof; trace/LDE/FRI trees row-sharded, iNTT/constraints/LDE/mix/openings column-sharded, "
+                             "proof download sharded (ms_stark_prove_multi, NCCL + CUDA IPC inside the library)") if world > 1 else "single GPU",
                  "config": f"SynthLinear AIR W={W} T={W} (C={C}), N=2^{args.log_rows}, blowup {B}, security {args.security_bits} bits, binary trees",
                  "stages_ms": {k: round(v, 3) for k, v in (stages or [])}}
-        if world > 1:
-            prove["sharded"] = getattr(ctx, "last_sharded_stats", None)
         del trace_cm
         if shared is not None:
             del proof_buf
             shared.close()
 
-    # ---- CPU baseline (rank 0): the oracle port, single thread, bounded sample ---------------------
+    # ---- extras (N = 1): BabyBear LDE, BASELINE configs 3a / 5a -----------------------------------------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        del out, coeffs, all_coeffs
+        torch.cuda.empty_cache()
+        cb = Context(BB, dev)
+        try:
+            cbb = cb.trace_synth(n, C, seed=1)
+            obb = cb.empty(C, L)
+            for _ in range(2):
+                cb.coset_lde(cbb, B, SHIFT % P[BB], out=obb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                cb.coset_lde(cbb, B, SHIFT % P[BB], out=obb)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_bb = e0.elapsed_time(e1) / args.steps
+            bytes_bb = (n + L) * C * 4
+            extras["babybear_lde"] = {"value": L * C / (ms_bb * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": ms_bb,
+                                      "roofline_frac": bytes_bb / (ms_bb * 1e-3) / 1e9 / peak, "algorithmic_bytes": bytes_bb,
+                                      "workload": f"babybear coset-LDE 2^{args.log_rows} x {C}, blowup {B} (u32)"}
+            del cbb, obb
+        finally:
+            cb.close()
+        torch.cuda.empty_cache()
+        cfgs = {}
+        for name, logn, w_, blow in (("3a: 2^20 x 16, blowup 8, binary trees", 20, 8, 8), ("5a: 2^24 x 64, blowup 4, binary trees", 24, 32, 4)):
+            from ministark_b200.synth import synth_linear_matrix
+
+            nn = 1 << logn
+            pr = StarkParams(args.security_bits, blow, nn - 1, 2 * w_, 2)
+            bd = int(ctx.lib.ms_stark_proof_bound(GL, pr, nn, 2 * w_))
+            try:
+                pbuf = torch.empty(bd, dtype=torch.uint8).pin_memory().numpy()
+                tcm = ctx.trace_synth(nn, w_, seed=SEED + 3)
+                mm = synth_linear_matrix(GL, nn, w_)
+                ts = []
+                for i in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    pl = ctx.stark_prove_device(pr, tcm, mm, pbuf)
+                    torch.cuda.synchronize()
+                    if i > 0:
+                        ts.append((time.perf_counter() - t0) * 1e3)
+                entry = {"prove_ms": float(np.mean(ts)), "proof_bytes": pl, "stages_ms": {k: round(v, 2) for k, v in ctx.last_timings()}}
+                if logn == 20:
+                    g3 = golden_digest("config3a_gl_2^20x16_b8")
+                    entry["matches_oracle_digest"] = bool(g3 and args.security_bits == 100 and hashlib.sha256(pbuf[:pl].tobytes()).hexdigest() == g3["proof_sha256"])
+                cfgs[name] = entry
+                del pbuf, tcm
+            except Exception as e:  # noqa: BLE001  (e.g. out of memory on a smaller part): report, do not fail the bench
+                cfgs[name] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+        extras["baseline_configs"] = cfgs
+        extras["baseline_configs_note"] = ("configs 3 and 5 as written (4-ary / 8-ary trees over 2^23 / 2^26 rows) are rejected like the "
+                                           "reference's MerkleTree::new would ('Tree is not full!', merkle.rs:93-104); these are the same "
+                                           "sizes with the binary trees StarkConfig::new builds (starks.rs:283-302)")
+
+    # ---- CPU baseline (rank 0, N = 1): the C restatement, single thread like the reference ---------------------
     cpu = None
-    if not args.no_cpu and rank == 0:
+    if not args.no_cpu and rank == 0 and world == 1:
+        from ministark_b200.synth import synth_linear_matrix, synth_trace
         from oracle import oracle as O
 
         O.build()
-        sample_cols = 2
-        cc = np.ascontiguousarray(synth_coeffs(n, C, 1)[:sample_cols])
-        t0 = time.perf_counter()
-        ref = O.coset_lde(GL, cc, L, SHIFT, threads=1)
-        dt = time.perf_counter() - t0
-        got = ctx.to_host(out[:sample_cols]) if rank == 0 else None
+        O.coset_lde(GL, synth_coeffs(GL, 1 << 16, 1, 1), 1 << 18, shift, threads=1)  # warm-up: page the library in
+        sample_cols, reps = 2, 2
+        cc = synth_coeffs(GL, n, sample_cols, 1)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ref = O.coset_lde(GL, cc, L, shift, threads=1)
+            ts.append(time.perf_counter() - t0)
+        c2 = Context(GL, dev)
+        got = c2.to_host(c2.coset_lde(c2.to_device(cc), B, shift))
         assert (got.T == ref).all(), "device LDE differs from the oracle on the sampled columns"
-        cpu = {"value": L * sample_cols / dt / 1e6, "unit": "Melem/s", "cores": 1, "kind": "port",
-               "sample": f"{sample_cols} of {C} columns, 2^{args.log_rows} -> 2^{args.log_rows + int(np.log2(B))} (oracle/liboracle.so, "
-                         f"single thread like the reference; {os.cpu_count()} host cores present); output compared bit-for-bit with the GPU's"}
+        # the whole prove, single thread, on the largest shape that stays near 10 s of CPU work
+        plog = min(args.log_rows, 16)
+        pn, pw = 1 << plog, C // 2
+        ptr, pm = synth_trace(GL, pn, pw, seed=SEED + 1), synth_linear_matrix(GL, pn, pw)
+        t0 = time.perf_counter()
+        praw, pstages = O.stark_prove(GL, args.security_bits, B, pn - 1, C, ptr, pm, threads=1, want_timings=True)
+        cpu_prove_ms = (time.perf_counter() - t0) * 1e3
+        pp = StarkParams(args.security_bits, B, pn - 1, C, 2)
+        pbuf = np.empty(int(c2.lib.ms_stark_proof_bound(GL, pp, pn, C)), dtype=np.uint8)
+        gts = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            raw = c2.stark_prove(pp, ptr, pm, capacity=pbuf.size)
+            if i > 0:
+                gts.append((time.perf_counter() - t0) * 1e3)
+        assert raw == praw.tobytes(), "GPU proof differs from the oracle's on the CPU-baseline shape"
+        c2.close()
+        cpu = {"value": L * sample_cols / float(np.mean(ts)) / 1e6, "unit": "Melem/s", "cores": 1, "kind": "port",
+               "samples_s": [round(v, 2) for v in ts],
+               "sample": f"{sample_cols} of {C} columns, 2^{args.log_rows} -> 2^{args.log_rows + int(np.log2(B))}, {reps} repetitions after a warm-up "
+                         f"(oracle/liboracle.so, single thread like the reference; {os.cpu_count()} host cores present); output compared "
+                         "bit-for-bit with the GPU's",
+               "prove": {"shape": f"2^{plog} rows x {C} cols, blowup {B}, {args.security_bits} bits", "cpu_prove_ms": cpu_prove_ms, "cores": 1,
+                         "gpu_prove_ms": float(np.mean(gts)), "speedup": cpu_prove_ms / float(np.mean(gts)),
+                         "cpu_stages_ms": {k: round(v, 1) for k, v in pstages.items()},
+                         "what": "C restatement of Stark::prove (oracle/prover.inc), host trace in -> proof bytes out on both sides; "
+                                 "proofs byte-identical"}}
 
     if rank == 0:
         bytes_alg = (n + L) * C * 8  # a4 algorithmic bytes = (N + L) * C * s per LDE
         lde_kernel_ms = sum(v[0] for k, v in kern.items()) / args.steps
         per_kernel = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in kern.items()}
         achieved = bytes_alg / (ms_step * 1e-3) / 1e9
+        ncu = ncu_summary("lde") if (args.log_rows, C, B, world) == (22, 32, 4, 1) else None
+        f_hz = (clocks or {}).get("sm_mhz") or 0.0
+        alu_peak = N_SM * INT32_LANES_PER_SM * f_hz * 1e6
+        alu = {"peak_thread_inst_per_s": alu_peak or None, "peak_source": f"{N_SM} SM x {INT32_LANES_PER_SM} INT32 lanes x {f_hz:.0f} MHz (median SM clock during the run)",
+               "achieved_thread_inst_per_s": None, "frac": None,
+               "note": "the LDE kernels are integer-issue bound (DESIGN.md 3.1): this is the fraction that says how close they run to their own ceiling; "
+                       "both INT pipes together could issue 2x this, register-operand bandwidth permitting"}
+        if ncu and alu_peak:
+            inst = float(ncu["thread_inst_executed_per_call"])
+            alu.update(achieved_thread_inst_per_s=inst / (ms_step * 1e-3), frac=inst / (ms_step * 1e-3) / alu_peak,
+                       inst_source=ncu.get("source"), thread_inst_per_call=inst, thread_inst_per_element=inst / (L * C))
         line = {
             "metric": "lde_melem_per_s", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(args),
                        "l2": "inputs (N*C*8) + outputs (L*C*8) exceed the 126 MB L2; no flush between iterations",
-                       "parallelism": f"{world} independent column shards"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES if (args.log_rows, C, B) == (22, 32, 4) else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, pass 1 + pass 2 "
-                                           "(profiles/r01_e_ncu_ntt.txt)",
+                       "parallelism": f"columns sharded over {world} rank(s): {[b_ - a_ for a_, b_ in column_ranges(C, world)]} columns each, no data-path collective"},
+            "prove_ms": prove["prove_ms"] if prove else None,
+            "roofline": {"bound": "hbm", "limiter": "int32-issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": float(ncu["dram_bytes_per_call"]) if ncu else None,
+                         "traffic_source": ncu.get("source") if ncu else "no ncu capture for this kernel source / shape: not reported",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
-                         "kernel": "coset-LDE = k_ntt_fixed pass 1 + pass 2 (+ twiddle builders), one ms_coset_lde call; "
-                                   "'launch' = that call, (N + L) * C * 8 algorithmic bytes",
-                         "kernels_ms_per_step": per_kernel, "kernel_sum_ms_per_step": lde_kernel_ms},
+                         "kernel": "coset-LDE = k_ntt_fixed pass 1 + pass 2, one ms_coset_lde call; 'launch' = that call, (N + L) * C * 8 algorithmic bytes",
+                         "kernels_ms_per_step": per_kernel, "kernel_sum_ms_per_step": lde_kernel_ms, "alu": alu},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if lde_weak:
+            line["lde_weak"] = lde_weak
         if cpu:
             line["cpu_baseline"] = cpu
         if prove:
             line["prove"] = prove
+        line.update(extras)
         print(json.dumps(line))
-    if dist is not None:
+    if world > 1:
+        ctx.comm_destroy()
         dist.destroy_process_group()
     ctx.close()
 

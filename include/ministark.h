@@ -88,6 +88,16 @@ int32_t ms_transpose_rm_to_cm(ms_ctx* ctx, const void* d_rowmajor, uint64_t rows
 /* Column-major -> row-major (for callers that want the reference's Matrix layout back). */
 int32_t ms_transpose_cm_to_rm(ms_ctx* ctx, const void* d_colmajor, uint64_t rows, uint64_t width, void* d_rowmajor);
 
+/* Trace generation on the device (column-major W x N, stride n), so that synthetic / recurrent AIRs never upload a trace:
+ * ms_trace_synth: element (row, col) = splitmix64(seed ^ (row*W + col)) mod p, the benchmark trace of SURVEY.md 8d
+ * (ministark_b200/synth.py synth_trace).  ms_trace_recurrence: rows [0, steps) follow row_{i+1} = M row_i from row0
+ * (M: host, W x W row-major canonical scalars, W <= 16), rows [steps, n) hold `padding` in every cell.
+ * Replaces: TraceTable::new + add_row as driven by a recurrent `Provable::trace`, src/air.rs:73-112
+ * (e.g. tests/e2e_goldilocks.rs:22-41 with M = [[0,1,0],[0,0,1],[0,1,1]], row0 = (1, b, 1 + b)). */
+int32_t ms_trace_synth(ms_ctx* ctx, uint64_t seed, uint64_t n, uint64_t w, void* d_trace_colmajor);
+int32_t ms_trace_recurrence(ms_ctx* ctx, const void* matrix_host, const void* row0_host, uint64_t w, uint64_t steps, uint64_t n,
+                            uint64_t padding, void* d_trace_colmajor);
+
 /* ---- a1 / a5 / a8: Merkle commitment ------------------------------------------------------ */
 /* MerkleTree::new over the ROW-MAJOR flattening of a column-major device matrix of `rows` x `width`
  * elements of `deg` coordinates each (deg = 1 base field, deg = D extension planes): leaf group g

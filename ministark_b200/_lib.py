@@ -55,6 +55,8 @@ SIGNATURES = {
     "ms_d2h": (_i32, [_vp, _vp, _vp, _sz]),
     "ms_transpose_rm_to_cm": (_i32, [_vp, _vp, _u64, _u64, _vp]),
     "ms_transpose_cm_to_rm": (_i32, [_vp, _vp, _u64, _u64, _vp]),
+    "ms_trace_synth": (_i32, [_vp, _u64, _u64, _u64, _vp]),
+    "ms_trace_recurrence": (_i32, [_vp, _vp, _vp, _u64, _u64, _u64, _u64, _vp]),
     "ms_merkle_commit": (_i32, [_vp, _vp, _u64, _u64, _u64, _i32, _u64, _u64, _vp, _vp]),
     "ms_merkle_node_count": (_u64, [_u64, _u64]),
     "ms_intt_columns": (_i32, [_vp, _vp, _u64, _u64, _u64, _vp, _u64]),

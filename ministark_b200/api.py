@@ -109,6 +109,22 @@ class Context:
     def _ptr(t):
         return C.c_void_p(t.data_ptr())
 
+    # ---------------------------------------------------------------- trace generation on the device (air.rs:73-112)
+    def trace_synth(self, n: int, w: int, seed: int = 0x5EED000000000000):
+        """the synthetic benchmark trace (synth.synth_trace) as a device [w, n] matrix, no upload"""
+        out = self.empty(w, n)
+        self._check(self.lib.ms_trace_synth(self.h, seed & (2**64 - 1), n, w, self._ptr(out)))
+        return out
+
+    def trace_recurrence(self, matrix, row0, steps: int, n: int, padding: int):
+        """rows [0, steps): row_{i+1} = M row_i; rows [steps, n): padding.  Device [w, n]."""
+        m = np.ascontiguousarray(matrix, dtype=self.np_dtype)
+        w = m.shape[0]
+        r0 = np.ascontiguousarray(row0, dtype=self.np_dtype)
+        out = self.empty(w, n)
+        self._check(self.lib.ms_trace_recurrence(self.h, m.ctypes.data, r0.ctypes.data, w, steps, n, int(padding), self._ptr(out)))
+        return out
+
     # ---------------------------------------------------------------- stages
     def transpose_rm_to_cm(self, rm):
         """[rows, width] row-major -> [width, rows] (air.rs:151-153 gather)."""

@@ -7,6 +7,7 @@
 #include "poly.cuh"
 #include "fri.cuh"
 #include "prover.cuh"
+#include "trace.cuh"
 
 using namespace ms;
 
@@ -251,6 +252,18 @@ int32_t ms_transpose_rm_to_cm(ms_ctx* c, const void* d_rm, uint64_t rows, uint64
 }
 int32_t ms_transpose_cm_to_rm(ms_ctx* c, const void* d_cm, uint64_t rows, uint64_t width, void* d_rm) {
 #define CALL(F) transpose<F>(c, (const F::T*)d_cm, (F::T*)d_rm, rows, width, false)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
+int32_t ms_trace_synth(ms_ctx* c, uint64_t seed, uint64_t n, uint64_t w, void* d_trace_cm) {
+#define CALL(F) trace_synth<F>(c, seed, n, w, (F::T*)d_trace_cm)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+int32_t ms_trace_recurrence(ms_ctx* c, const void* matrix_host, const void* row0_host, uint64_t w, uint64_t steps, uint64_t n, uint64_t padding,
+                            void* d_trace_cm) {
+#define CALL(F) trace_recurrence<F>(c, (const F::T*)matrix_host, (const F::T*)row0_host, w, steps, n, (F::T)(padding % (uint64_t)F::P), (F::T*)d_trace_cm)
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }

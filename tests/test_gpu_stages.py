@@ -229,3 +229,33 @@ def test_butterfly_arithmetic_selftest(field, ctxs):
     bad = C.c_uint64(123)
     ctxs[field]._check(ctxs[field].lib.ms_selftest_field_ops(ctxs[field].h, 1 << 20, C.byref(bad)))
     assert bad.value == 0
+
+
+@pytest.mark.parametrize("field", [GL, BB])
+def test_trace_generation_on_the_device(field, ctxs, pyref):
+    """ms_trace_synth equals the host generator of ministark_b200/synth.py; ms_trace_recurrence equals the Fibonacci
+    trace TraceTable::new + add_row build on the host (tests/e2e_goldilocks.rs:22-41, src/air.rs:73-112), padding rows
+    included, and a long recurrence equals the row-by-row host loop."""
+    from ministark_b200.synth import synth_trace
+
+    ctx = ctxs[field]
+    p = P[field]
+    for n, w, seed in ((16, 3, 5), (1 << 12, 8, 0x5EED000000000001), (1 << 10, 33, 2**64 - 1)):
+        assert (ctx.to_host(ctx.trace_synth(n, w, seed=seed)) == synth_trace(field, n, w, seed=seed).T).all()
+    F = pyref.FIELDS[field]
+    steps = 9 if field == GL else 7
+    t = pyref.FibonacciClaim(F, steps).trace(2)
+    want = np.array(t.data, dtype=np.uint64).reshape(t.length, 3)
+    fib = [[0, 1, 0], [0, 0, 1], [0, 1, 1]]
+    got = ctx.to_host(ctx.trace_recurrence(fib, [1, 2, 3], steps, t.length, int(t.data[-1])))
+    assert (got.T == want).all()
+    n, steps = 1 << 13, (1 << 13) - 1
+    m = [[3, p - 1, 0, 7], [0, 0, 1, 0], [5, 0, 0, 1], [1, 1, 1, 1]]
+    row = [1, 2, 3, 4]
+    rows = []
+    for _ in range(steps):
+        rows.append(row)
+        row = [sum(a * b for a, b in zip(mr, row)) % p for mr in m]
+    got = ctx.to_host(ctx.trace_recurrence(m, [1, 2, 3, 4], steps, n, 77))
+    assert (got[:, :steps].T.astype(object) == np.array(rows, dtype=object)).all()
+    assert (got[:, steps:] == 77).all()

@@ -1,8 +1,8 @@
 """Per-stage device timings (CUDA events) on the headline shape; used for A/B builds via MINISTARK_LIB."""
 import sys, time, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from ministark_b200 import Context
-from tests.synth import synth_trace
+from ministark_b200.synth import synth_trace
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 4

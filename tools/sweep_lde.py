@@ -1,9 +1,9 @@
 """BASELINE config 4: batched coset-LDE sweep 2^16..2^24 rows x 64 cols, blowup 4, Goldilocks and BabyBear,
 device-resident, CUDA events; prints one JSON line per point with the HBM-roofline fraction."""
 import json, sys, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from ministark_b200 import Context
-from tests.synth import synth_trace
+from ministark_b200.synth import synth_trace
 peak = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'] if __import__('os').path.exists('MEASURED_PEAKS.json') else 6650.0
 cols, B = 64, 4
 lo, hi = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (16, 24)
