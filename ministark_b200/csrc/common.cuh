@@ -43,6 +43,14 @@ struct Ctx {
     // multi-GPU: the communicator this context is a rank of (nullptr: single GPU) and which stages shard
     Comm* comm = nullptr;
     int shard_mask = MS_SHARD_ALL;
+    struct NttTables {  // last two-pass transform's inter-pass factor table and coset block twiddles (ntt.cuh lde_batch)
+        void* ft = nullptr;
+        void* tw = nullptr;
+        int logN = -1, logB = 0, inverse = 0, tile = 0, field = -1;
+        uint64_t shift = 0;
+    } ntt_tables;
+    int lde_linearity = 1;  // prover: constraint columns of the LDE by linearity when the constraint matrix is sparse (prover.cuh)
+    int ntt_log_tile = 13;  // log2 elements of an NTT tile (ntt.cuh NTT_LOG_TILE_PREF); MINISTARK_NTT_TILE=12 selects half tiles
 };
 
 inline int fail(Ctx* c, int code, const char* fmt, ...) {

@@ -130,6 +130,11 @@ int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out)
     ms_ctx* c = new ms_ctx();
     c->field = field;
     c->device = device;
+    if (const char* e = getenv("MINISTARK_LDE_LINEARITY")) c->lde_linearity = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("MINISTARK_NTT_TILE")) {
+        const int v = atoi(e);
+        if (v == NTT_LOG_TILE_PREF || v == NTT_LOG_TILE_PREF - 1) c->ntt_log_tile = v;
+    }
     // NULL = the legacy default stream (what torch uses unless told otherwise), so that the caller's
     // copies and this library's kernels are ordered without extra synchronisation
     c->stream = reinterpret_cast<cudaStream_t>(stream);
@@ -156,6 +161,8 @@ void ms_ctx_destroy(ms_ctx* c) {
     for (int i = 0; i < 2; i++)
         for (int a = 0; a < 16; a++)
             if (c->tw16_plain[i][a]) cudaFree(c->tw16_plain[i][a]);
+    if (c->ntt_tables.ft) cudaFree(c->ntt_tables.ft);
+    if (c->ntt_tables.tw) cudaFree(c->ntt_tables.tw);
     if (c->dec4) cudaFree(c->dec4);
     if (c->hstage) cudaFreeHost(c->hstage);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -853,8 +853,7 @@ struct NttPlan {
 // Tiles hold 2^NTT_LOG_TILE_PREF elements.  Pass 1 batches extra m1 when the cosets do not fill a tile and
 // splits the cosets over several tiles when they overflow it; pass 2 takes whatever number of consecutive
 // (k2, coset) lanes fills a tile (fewer than B lanes for the largest transforms).
-inline bool ntt_plan(int logN, int logB, NttPlan* p) {
-    const int T = NTT_LOG_TILE_PREF;
+inline bool ntt_plan(int logN, int logB, NttPlan* p, int T = NTT_LOG_TILE_PREF) {
     if (logN + logB <= T) {
         *p = {logN, 0, logB, 0, 0, 0};
         return true;
@@ -883,7 +882,9 @@ inline bool ntt_plan(int logN, int logB, NttPlan* p) {
 }
 
 // tile shapes with a compile-time specialisation
-#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0)
+// (A + BETA = 13: 8192-element tiles, 256 threads, 3 CTAs / SM; A + BETA = 12: 4096-element tiles, 128 threads, 6 CTAs / SM --
+// the same warps per SM in CTAs half the size: barriers couple fewer warps and load / compute phases of more CTAs interleave)
+#define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(8, 4) X(9, 3) X(10, 2) X(11, 1) X(12, 0)
 // does launch_tile run this tile through k_ntt_fixed (and, for Goldilocks, with block twiddles)?
 template <class F>
 inline bool tile_is_fixed(const NttTile<F>& g) {
@@ -900,9 +901,14 @@ int launch_fixed_dir(Ctx* c, const NttTile<F>& g, const char* name) {
     using T = typename F::T;
     constexpr size_t smem = sizeof(T) << (A + BETA);
     constexpr bool big = smem > 100 * 1024;  // one CTA per SM: give it 512 threads
-    constexpr int threads = big ? 512 : 256;
-    auto kern = k_ntt_fixed<F, A, BETA, threads, big ? 1 : MS_NTT_MINB, INV>;
-    MS_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr bool half = A + BETA == NTT_LOG_TILE_PREF - 1;
+    constexpr int threads = big ? 512 : (half ? NTT_THREADS / 2 : NTT_THREADS);
+    auto kern = k_ntt_fixed<F, A, BETA, threads, big ? 1 : (half ? 2 * MS_NTT_MINB : MS_NTT_MINB), INV>;
+    static uint64_t attr_done = 0;  // per instantiation: devices whose function attribute is set (once, not per launch)
+    if (!(attr_done >> (c->device & 63) & 1)) {
+        MS_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done |= 1ULL << (c->device & 63);
+    }
     prof_begin(c, name);
     kern<<<g.cols * g.tiles, threads, smem, c->stream>>>(g);
     prof_end(c);
@@ -979,7 +985,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     if (inverse && logB != 0) return fail(c, MS_ERR_UNSUPPORTED, "inverse transform with blowup");
     if (cols >= (1ULL << 20)) return fail(c, MS_ERR_UNSUPPORTED, "too many columns");
     NttPlan pl;
-    if (!ntt_plan(logN, logB, &pl)) return fail(c, MS_ERR_UNSUPPORTED, "transform 2^%d x blowup 2^%d too large", logN, logB);
+    if (!ntt_plan(logN, logB, &pl, c->ntt_log_tile)) return fail(c, MS_ERR_UNSUPPORTED, "transform 2^%d x blowup 2^%d too large", logN, logB);
     MS_TRY(ensure_wtab<F>(c, inverse ? 1 : 0));
     const T* wtab = reinterpret_cast<const T*>(c->wtab[inverse ? 1 : 0]);
     const int B = 1 << logB;
@@ -1004,7 +1010,13 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
         }
         sj = F::mul(sj, wL);
     }
-    Scratch consts(c), t1(c), ft(c), tmp(c);
+    Scratch consts(c), t1(c), tmp(c);
+    // The coset block-twiddle table and the inter-pass factor table only depend on (n, blowup, shift, direction, tile size):
+    // they are kept for the next call with the same key (the prover extends its columns in several calls per proof, a
+    // benchmark repeats one call), built on this stream and only ever used on it.
+    Ctx::NttTables& tc = c->ntt_tables;
+    const bool tc_hit = tc.ft && tc.logN == logN && tc.logB == logB && tc.shift == (uint64_t)shift && tc.inverse == (inverse ? 1 : 0) &&
+                        tc.tile == c->ntt_log_tile && tc.field == F::ID;
     // geometry of the first pass decides which kernel runs it, and with it the twiddle-table format
     NttTile<F> g1{};
     g1.a = pl.a;
@@ -1021,7 +1033,26 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     }
     const T* d_shifts = consts.p ? consts.as<T>() + (size_t)B * na : nullptr;
     uint32_t jstride1 = plain ? 0u : (1u << pl.a);
-    if (blocks1) {
+    if (blocks1 && !plain && two) {
+        // cached with the factor table below (same key)
+        if (!tc_hit) {
+            if (tc.tw) cudaFreeAsync(tc.tw, c->stream);  // stream-ordered: earlier launches that read it are ahead of the free
+            tc.tw = nullptr;
+            MS_CUDA(c, cudaMallocAsync(&tc.tw, ((size_t)B << (pl.a + 1)) * sizeof(T), c->stream));
+            TwRoots<F> roots{};
+            for (int l = 0; l <= NTT_MAXLOG; l++) {
+                T g = (l <= F::TWO_ADICITY) ? root_of_unity<F>(l) : (T)1;
+                roots.w[l] = inverse ? finv<F>(g) : g;
+            }
+            const unsigned nn = (unsigned)B << (pl.a + 1);
+            prof_begin(c, "k_build_tw16");
+            k_build_tw16<F><<<(nn + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<T*>(tc.tw), d_shifts, roots, pl.a, B, pl.b);
+            prof_end(c);
+            MS_LAUNCH_CHECK(c);
+        }
+        d_tw1 = reinterpret_cast<const T*>(tc.tw);
+        jstride1 = 2u << pl.a;
+    } else if (blocks1) {
         MS_TRY(get_tw16<F>(c, pl.a, inverse, plain ? nullptr : d_shifts, B, pl.b, &t1, &d_tw1));
         jstride1 = plain ? 0u : (2u << pl.a);
     } else if (!plain) {
@@ -1036,14 +1067,20 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     const bool inplace = two && pl.logR1 == 0 && tile_rounds(pl.b) >= 2;
     const int lay1 = pl.logR1 + logB;  // low index bits (m1 offset, coset) of the intermediate layout
     if (two) {
-        MS_TRY(ft.alloc(((size_t)N << logB) * sizeof(T)));
-        int chunk_log = pl.a < 6 ? pl.a : 6;
-        uint64_t threads = (((uint64_t)1 << pl.b) << logB) * ((1ULL << pl.a) >> chunk_log);
-        prof_begin(c, "k_build_ft");
-        k_build_ft<F><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(ft.as<T>(), d_shifts, wN, scale, pl.a, pl.b, logB,
-                                                                               pl.logR1, chunk_log);
-        prof_end(c);
-        MS_LAUNCH_CHECK(c);
+        if (!tc_hit) {
+            if (tc.ft) cudaFreeAsync(tc.ft, c->stream);
+            tc.ft = nullptr;
+            tc.logN = -1;
+            MS_CUDA(c, cudaMallocAsync(&tc.ft, ((size_t)N << logB) * sizeof(T), c->stream));
+            int chunk_log = pl.a < 6 ? pl.a : 6;
+            uint64_t threads = (((uint64_t)1 << pl.b) << logB) * ((1ULL << pl.a) >> chunk_log);
+            prof_begin(c, "k_build_ft");
+            k_build_ft<F><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<T*>(tc.ft), d_shifts, wN, scale, pl.a, pl.b,
+                                                                                   logB, pl.logR1, chunk_log);
+            prof_end(c);
+            MS_LAUNCH_CHECK(c);
+            tc.logN = logN; tc.logB = logB; tc.shift = (uint64_t)shift; tc.inverse = inverse ? 1 : 0; tc.tile = c->ntt_log_tile; tc.field = F::ID;
+        }
         if (!inplace) MS_TRY(tmp.alloc(cols * ((size_t)N << logB) * sizeof(T)));
     }
     g1.src = d_in;
@@ -1051,7 +1088,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     g1.dst = two ? (inplace ? d_out : tmp.as<T>()) : d_out;
     g1.dst_stride = two ? (inplace ? out_stride : ((uint64_t)N << logB)) : out_stride;
     g1.tw = d_tw1;
-    g1.ft = two ? ft.as<T>() : nullptr;
+    g1.ft = two ? reinterpret_cast<const T*>(tc.ft) : nullptr;
     g1.scale = Fast<F>::to_tw(scale);
     g1.has_scale = (!two && scale != 1) ? 1 : 0;
     g1.a = pl.a;

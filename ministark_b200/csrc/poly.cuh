@@ -89,6 +89,75 @@ int linear_constraints_gather(Ctx* c, const typename F::T* const* d_cols, uint64
     return MS_OK;
 }
 
+// Sparse rows (at most 4 non-zero entries each: every AIR of the reference's tests, and the synthetic one): a row is a
+// short list of (column, scalar) pairs, +1 / -1 scalars cost an add / a sub instead of a product, and a thread handles two
+// consecutive elements with 16-byte loads.  Same values as k_linear_constraints (exact arithmetic).
+constexpr int LIN_MAX_NNZ = 4;
+template <class F>
+struct SparseRow {
+    int nnz;
+    int col[LIN_MAX_NNZ];
+    typename F::T val[LIN_MAX_NNZ];
+};
+template <class F>
+__global__ void k_linear_sparse(const typename F::T* const* __restrict__ cols, uint64_t n, const SparseRow<F>* __restrict__ rows, int t,
+                                typename F::T* __restrict__ out, uint64_t out_stride) {
+    using T = typename F::T;
+    const uint64_t m = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (m >= n) return;
+    const bool pair = m + 1 < n;
+    for (int r = 0; r < t; r++) {
+        const SparseRow<F> row = rows[r];  // warp-uniform
+        T a0 = 0, a1 = 0;
+        for (int e = 0; e < row.nnz; e++) {
+            const T* __restrict__ src = cols[row.col[e]];
+            T v0 = src[m], v1 = pair ? src[m + 1] : (T)0;
+            const T sc = row.val[e];
+            if (sc == 1) { a0 = F::add(a0, v0); a1 = F::add(a1, v1); }
+            else if (sc == (T)(F::P - 1)) { a0 = F::sub(a0, v0); a1 = F::sub(a1, v1); }
+            else { a0 = F::add(a0, F::mul(sc, v0)); a1 = F::add(a1, F::mul(sc, v1)); }
+        }
+        out[(uint64_t)r * out_stride + m] = a0;
+        if (pair) out[(uint64_t)r * out_stride + m + 1] = a1;
+    }
+}
+// rows of the host matrix applied to the columns of the device pointer table; false when a row has too many entries
+template <class F>
+bool sparse_rows(const typename F::T* mat_rows_host, uint64_t t, uint64_t w, std::vector<SparseRow<F>>* out) {
+    out->assign(t, SparseRow<F>{});
+    for (uint64_t r = 0; r < t; r++) {
+        SparseRow<F>& row = (*out)[r];
+        for (uint64_t j = 0; j < w; j++) {
+            const typename F::T v = (typename F::T)((uint64_t)mat_rows_host[r * w + j] % (uint64_t)F::P);
+            if (!v) continue;
+            if (row.nnz == LIN_MAX_NNZ) return false;
+            row.col[row.nnz] = (int)j;
+            row.val[row.nnz++] = v;
+        }
+    }
+    return true;
+}
+template <class F>
+int linear_sparse(Ctx* c, const typename F::T* const* d_cols, uint64_t n, const std::vector<SparseRow<F>>& rows, typename F::T* d_out,
+                  uint64_t out_stride) {
+    if (rows.empty() || n == 0) return MS_OK;
+    Scratch dr(c);
+    const size_t bytes = rows.size() * sizeof(SparseRow<F>);
+    MS_TRY(dr.alloc(bytes));
+    MS_TRY(stage_from_host(c, rows.data(), bytes, dr.p));
+    k_linear_sparse<F><<<(unsigned)((n / 2 + 256) / 256), 256, 0, c->stream>>>(d_cols, n, dr.as<SparseRow<F>>(), (int)rows.size(), d_out, out_stride);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+// pointer table of `w` columns of a contiguous column-major matrix
+template <class F>
+int column_table(Ctx* c, const typename F::T* base, uint64_t stride, uint64_t w, Scratch* tab) {
+    std::vector<const typename F::T*> cols(w);
+    for (uint64_t j = 0; j < w; j++) cols[j] = base + j * stride;
+    MS_TRY(tab->alloc(w * sizeof(void*)));
+    return stage_from_host(c, cols.data(), w * sizeof(void*), tab->p);
+}
+
 // ------------------------------------------------------------------------------------------ a6
 // A rank's share of the mix: out[m] = r0a * sum_{i<na} r^i a_i[m] + r0b * sum_{i<nb} r^i b_i[m]  (two runs of
 // consecutive columns with their starting powers r0 = r^(global index of the run's first column)).

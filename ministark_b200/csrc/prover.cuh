@@ -230,6 +230,13 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         *first = a;
         return g;
     };
+    // The LDE is linear, and every constraint column is a fixed linear combination of trace columns (the T x W matrix):
+    // when the matrix is sparse (the e2e / synthetic AIRs use 2-3 trace columns per constraint) the constraint columns of the
+    // LDE are that same combination of the trace columns' evaluations -- one streaming pass instead of T more transforms,
+    // bit-identical because the arithmetic is exact.  (Dense matrices keep the transforms.)
+    std::vector<SparseRow<F>> srows;
+    const bool sparse = t > 0 && sparse_rows<F>(cmat_host, t, w, &srows);
+    const bool lde_by_linearity = sparse && c->lde_linearity;
     StageTimer tm(c, ps);
     IOPattern io = stark_iopattern(F::BITS, D, R, Q, QF);
     Merlin merlin(io, c->bridge_masks, c->leftover_as_published != 0);
@@ -304,7 +311,8 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             }
             MS_TRY(ptab.alloc(w * sizeof(void*)));
             MS_TRY(stage_from_host(c, cols.data(), w * sizeof(void*), ptab.p));
-            MS_TRY(linear_constraints_gather<F>(c, ptab.as<const T*>(), n, w, cmat_host + ta * w, nt, my_cons_coef, n));  // air.rs:130-134, own rows
+            if (sparse) MS_TRY(linear_sparse<F>(c, ptab.as<const T*>(), n, std::vector<SparseRow<F>>(srows.begin() + ta, srows.begin() + tb), my_cons_coef, n));
+            else MS_TRY(linear_constraints_gather<F>(c, ptab.as<const T*>(), n, w, cmat_host + ta * w, nt, my_cons_coef, n));  // air.rs:130-134, own rows
         }
         tm.end();
     } else {
@@ -314,7 +322,12 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         MS_TRY(lde_batch<F>(c, d_trace, n, w, ilog2(n), 0, (T)1, true, coeffs.as<T>(), n));  // air.rs:147-160
         tm.end();
         tm.begin("constraints");
-        MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
+        if (sparse) {
+            MS_TRY(column_table<F>(c, coeffs.as<T>(), n, w, &ptab));
+            MS_TRY(linear_sparse<F>(c, ptab.as<const T*>(), n, srows, coeffs.as<T>() + w * n, n));  // air.rs:130-134
+        } else {
+            MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
+        }
         tm.end();
     }
     if (hooks && hooks->lde_commit) {
@@ -326,7 +339,22 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         T* my_lde = reinterpret_cast<T*>(arena_of(rank, off_b));  // [nw + nt][L]: own trace columns, then own constraint columns
         tm.begin("lde");
         MS_TRY(lde_batch<F>(c, my_trace_coef, n, nw, ilog2(n), ilog2(B), shift, false, my_lde, L));                 // starks.rs:87-91
-        MS_TRY(lde_batch<F>(c, my_cons_coef, n, nt, ilog2(n), ilog2(B), shift, false, my_lde + nw * L, L));
+        if (lde_by_linearity) MS_TRY(cm->barrier(c));  // (every rank: collectives are never conditional on a rank's share)
+        if (lde_by_linearity && nt) {
+            // the trace columns' evaluations of every rank are complete: combine them pointwise
+            std::vector<const T*> cols(w);
+            for (uint64_t j = 0; j < w; j++) {
+                uint64_t first;
+                const int g = w_owner(j, &first);
+                cols[j] = reinterpret_cast<const T*>(arena_of(g, off_b)) + (j - first) * L;
+            }
+            Scratch etab(c);
+            MS_TRY(etab.alloc(w * sizeof(void*)));
+            MS_TRY(stage_from_host(c, cols.data(), w * sizeof(void*), etab.p));
+            MS_TRY(linear_sparse<F>(c, etab.as<const T*>(), L, std::vector<SparseRow<F>>(srows.begin() + ta, srows.begin() + tb), my_lde + nw * L, L));
+        } else if (!lde_by_linearity) {
+            MS_TRY(lde_batch<F>(c, my_cons_coef, n, nt, ilog2(n), ilog2(B), shift, false, my_lde + nw * L, L));
+        }
         tm.end();
         tm.begin("lde_commit");
         MS_TRY(cm->barrier(c));  // every rank's columns are complete before anyone reads them
@@ -357,7 +385,14 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     } else {
         MS_TRY(lde.alloc(C * L * sizeof(T)));
         tm.begin("lde");
-        MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, C, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91
+        if (lde_by_linearity) {
+            MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, w, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91, trace columns
+            Scratch etab(c);
+            MS_TRY(column_table<F>(c, lde.as<T>(), L, w, &etab));
+            MS_TRY(linear_sparse<F>(c, etab.as<const T*>(), L, srows, lde.as<T>() + w * L, L));               // constraint columns, pointwise
+        } else {
+            MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, C, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91
+        }
         tm.end();
         tm.begin("lde_commit");
         MS_TRY(merkle_commit<F>(c, lde.as<T>(), L, L, C, 1, lpn, kk, nullptr, lde_root));  // starks.rs:92-94

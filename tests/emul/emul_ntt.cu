@@ -52,7 +52,7 @@ static void run_fixed(const NttTile<F>& g) {
     }
 }
 // the shapes the emulation runs through the fixed-shape body: the product's (MS_NTT_FIXED_SHAPES) plus small ones
-#define EMU_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(5, 2) X(6, 0) X(7, 3) X(5, 1) X(7, 1)
+#define EMU_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(8, 4) X(9, 3) X(10, 2) X(11, 1) X(12, 0) X(5, 2) X(6, 0) X(7, 3) X(5, 1) X(7, 1)
 template <class F>
 static bool emu_is_fixed(const NttTile<F>& g) {
     if (!(g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0))) return false;
@@ -62,6 +62,7 @@ static bool emu_is_fixed(const NttTile<F>& g) {
     return false;
 }
 static int g_fixed_used = 0;
+static int g_tile_log = NTT_LOG_TILE_PREF;  // the planner's tile size (Ctx::ntt_log_tile in the product)
 template <class F>
 static void run_any(const NttTile<F>& g) {
     if (emu_is_fixed<F>(g)) {
@@ -99,7 +100,7 @@ static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, 
                                           typename F::T shift, bool inverse, int force_a) {
     using T = typename F::T;
     NttPlan pl;
-    if (!ntt_plan(logN, logB, &pl)) { printf("plan failed\n"); exit(2); }
+    if (!ntt_plan(logN, logB, &pl, g_tile_log)) { printf("plan failed\n"); exit(2); }
     if (force_a >= 0) {  // exercise two-pass geometry on small sizes
         pl.a = force_a; pl.b = logN - force_a;
         pl.logR1 = 0; pl.cs1 = 0; pl.beta1 = logB; pl.beta2 = logB;
@@ -279,6 +280,19 @@ int main() {
     bad += check<BB>(12, 2, false, 7, 1);
     bad += check<GL>(23, 2, false, -1, 1);   // planner's own coset split: (12,1) + (11,2)
     bad += check<GL>(14, 0, true, -1, 1);
+    // half-size tiles (MINISTARK_NTT_TILE=12): 4096-element tiles, the headline shape becomes (11,1) + (11,1) with the cosets
+    // split over two pass-1 tiles
+    g_tile_log = NTT_LOG_TILE_PREF - 1;
+    bad += check<GL>(22, 2, false, -1, 1);
+    bad += check<GL>(16, 2, false, -1, 1);
+    bad += check<BB>(16, 2, false, -1, 1);
+    bad += check<GL>(17, 3, false, -1, 1);
+    bad += check<GL>(11, 2, false, -1, 1);
+    bad += check<GL>(12, 0, false, -1, 2);
+    bad += check<GL>(18, 0, true, -1, 1);
+    bad += check<BB>(20, 1, false, -1, 1);
+    bad += check<GL>(24, 2, false, -1, 1);
+    g_tile_log = NTT_LOG_TILE_PREF;
     printf("fixed-shape tiles used: %d\n", g_fixed_used);
     printf(bad ? "FAILED\n" : "ALL OK\n");
     return bad ? 1 : 0;
