@@ -232,6 +232,18 @@ typedef struct ms_commit_hooks {
 int32_t ms_stark_prove_hooked(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
                               const void* constraint_matrix_host, uint64_t t, const ms_commit_hooks* hooks,
                               uint8_t* proof_out, uint64_t* proof_len);
+/* Stark::verify on the canonical proof dump.  d_constrains_colmajor: what the reference's caller passes as `constrains`
+ * (the Constrains object: the W trace polynomials followed by the T constraint polynomials), as `cols` coefficient columns of
+ * length n on the device.  The constraint polynomials are re-evaluated at the Q query points on the device; the transcript
+ * replay, the FRI consistency checks and the Merkle paths run on the host.  *accepted = 1 / 0; *failed_check (optional) = the
+ * reference line of the first failed check (0 accepted, -2 malformed dump).  strict != 0 also enforces the Merkle paths, which
+ * the reference computes and discards (src/fri.rs:237,239).
+ * Replaces: Stark::verify, src/starks.rs:171-235, with Fri::verify, src/fri.rs:191-281, and MerkleRoot::check_proof,
+ * src/merkle.rs:312-338. */
+int32_t ms_stark_verify(ms_ctx* ctx, const ms_stark_params* p, const void* d_constrains_colmajor, uint64_t stride, uint64_t n,
+                        uint64_t cols, const uint8_t* proof, uint64_t proof_len, int32_t strict, int32_t* accepted,
+                        int32_t* failed_check);
+
 /* ---- multi-GPU inside the library (csrc/comm.cuh, csrc/prover.cuh) ----------------------------------------
  * One prover replica per GPU.  Bind every rank's context to a communicator, then call ms_stark_prove_multi (or any
  * ms_stark_prove*) on all ranks with the same arguments: the trace tree, iNTT, constraints, LDE + its tree, mixing, DEEP

@@ -74,6 +74,7 @@ SIGNATURES = {
     "ms_stark_prove": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_device": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_hooked": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
+    "ms_stark_verify": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _u64, _vp, _u64, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "ms_comm_unique_id": (_i32, [_vp]),
     "ms_comm_init_nccl": (_i32, [_vp, _vp, _i32, _i32]),
     "ms_comm_init_local": (_i32, [C.POINTER(_vp), _i32]),

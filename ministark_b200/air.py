@@ -163,6 +163,46 @@ class TraceTable:
         return M
 
 
+    def derive_constrains(self, ctx=None) -> "Constrains":
+        """air.rs:127-144: the trace polynomials (iNTT of every column, air.rs:147-160) followed by the transition
+        polynomials, computed on the device (ms_intt_columns + ms_linear_constraints) and kept there."""
+        from .api import Context
+
+        ctx = ctx or Context(self.F.field_id)
+        trace_cm = ctx.to_device(np.ascontiguousarray(self.data.T))
+        polys = ctx.intt_columns(trace_cm)
+        m = self.linear_matrix()
+        if m.shape[0]:
+            import torch
+
+            polys = torch.cat([polys, ctx.linear_constraints(polys, m)], dim=0)
+        return Constrains(self.width, m.shape[0], polys, ctx)
+
+
+class Constrains:
+    """air.rs:163-186: the constraint polynomials (trace polynomials first), here a device matrix [C, N] of
+    coefficient columns (trailing zeros kept; `get_constrain_poly` trims like DensePolynomial does)."""
+
+    def __init__(self, trace_constrains_num: int, transition_constrains_num: int, polys, ctx):
+        self.trace_constrains_num, self.transition_constrains_num = trace_constrains_num, transition_constrains_num
+        self.polys, self.ctx = polys, ctx
+
+    def __len__(self):  # air.rs:169-171
+        return self.polys.shape[0]
+
+    def is_empty(self):  # air.rs:173-175
+        return len(self) == 0
+
+    def get_constrain_poly(self, index: int) -> List[int]:  # air.rs:178-181
+        c = [int(v) for v in self.ctx.to_host(self.polys[index])]
+        while c and c[-1] == 0:
+            c.pop()
+        return c
+
+    def get_polynomials(self):  # air.rs:183-185
+        return self.polys
+
+
 class Provable:
     """air.rs:9-12: `fn trace(&self, witness: &W) -> TraceTable<F>`."""
 

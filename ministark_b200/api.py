@@ -284,6 +284,16 @@ class Context:
                                                    out.ctypes.data, C.byref(cap)))
         return int(cap.value)
 
+    def stark_verify(self, params: StarkParams, constrains_cm, proof: bytes, strict: bool = False) -> Tuple[bool, int]:
+        """Stark::verify (starks.rs:171-235).  constrains_cm: device [C, N] coefficient columns (the Constrains object).
+        Returns (accepted, reference line of the first failed check)."""
+        cols, n = constrains_cm.shape
+        raw = np.frombuffer(proof, dtype=np.uint8) if not isinstance(proof, np.ndarray) else proof
+        ok, line = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.ms_stark_verify(self.h, C.byref(params), self._ptr(constrains_cm), constrains_cm.stride(0), n, cols,
+                                             raw.ctypes.data, raw.size, int(strict), C.byref(ok), C.byref(line)))
+        return bool(ok.value), int(line.value)
+
     # ---------------------------------------------------------------- multi-GPU (csrc/comm.cuh)
     @staticmethod
     def comm_unique_id() -> bytes:

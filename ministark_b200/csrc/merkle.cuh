@@ -268,7 +268,7 @@ __device__ __forceinline__ void node_hash_one(const uint32_t* children, uint32_t
 // levels separated by __syncthreads (the ~log_k(lv) launches it replaces cost more than the hashing).
 // `nodes` points at the first digest of the starting level; the levels follow each other as in d_nodes.
 constexpr int TOP_THREADS = 512;
-constexpr uint64_t TOP_NODES = 4096;
+constexpr uint64_t TOP_NODES = 512;  // (a 4096-digest start costs 16 sequential hash times in the one CTA, 65 us per tree; 512: 9, the three wider levels go through k_node_hash)
 template <int K>
 __global__ void __launch_bounds__(TOP_THREADS)
 k_tree_top(uint32_t* nodes, uint64_t lv, uint64_t stop) {

@@ -8,6 +8,7 @@
 #include "fri.cuh"
 #include "prover.cuh"
 #include "trace.cuh"
+#include "verifier.cuh"
 
 using namespace ms;
 
@@ -398,6 +399,13 @@ int32_t ms_stark_prove_hooked(ms_ctx* c, const ms_stark_params* p, const void* d
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }
+int32_t ms_stark_verify(ms_ctx* c, const ms_stark_params* p, const void* d_constrains_cm, uint64_t stride, uint64_t n, uint64_t cols,
+                        const uint8_t* proof, uint64_t proof_len, int32_t strict, int32_t* accepted, int32_t* failed_check) {
+#define CALL(F) stark_verify<F>(c, *p, (const F::T*)d_constrains_cm, stride, n, cols, proof, proof_len, strict, accepted, failed_check)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
+
 /* ---- multi-GPU: communicators (csrc/comm.cuh) -------------------------------------------------- */
 int32_t ms_comm_unique_id(uint8_t id128[128]) {
     NcclApi& api = nccl_api();

@@ -120,7 +120,12 @@ class Stark:
     def proof_bound(self, n: int, cols: int) -> int:
         return int(_lib.load().ms_stark_proof_bound(self.config.field.field_id, C.byref(self.config.params), n, cols))
 
-    def verify(self, constrains, proof) -> bool:
-        raise NotImplementedError(
-            "Stark::verify (starks.rs:171-235) is outside the accelerated path (SURVEY.md section 8: host oracle only); "
-            "use the reference verifier, or oracle/pyref.py in tests")
+    def verify(self, constrains, proof, strict: bool = False) -> bool:
+        """Stark::verify (starks.rs:171-235): `constrains` is the Constrains object of `TraceTable.derive_constrains`,
+        `proof` a StarkProof (its canonical dump is what crosses the C ABI).  Returns Ok(true) / raises on a failed
+        assertion like the reference (its checks are `assert!`s).  strict also enforces the Merkle paths."""
+        raw = proof.raw if isinstance(proof, StarkProof) else bytes(proof)
+        ok, line = self.ctx.stark_verify(self.config.params, constrains.get_polynomials(), raw, strict=strict)
+        if not ok:
+            raise AssertionError(f"Stark::verify: check at reference line {line} failed" if line > 0 else "malformed proof dump")
+        return True

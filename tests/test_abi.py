@@ -135,13 +135,29 @@ def test_proof_dump_parser_round_trips_the_oracle_proofs(name, steps, pyref):
             assert [norm(e) for e in gq] == [norm(e) for e in rq]
 
 
-def test_integration_doc_binds_every_declared_symbol():
-    """INTEGRATION.md's Rust `extern "C"` block (what a maintainer of the reference adds) names every entry point
-    include/ministark.h declares."""
-    with open(os.path.join(ROOT, "INTEGRATION.md")) as fh:
-        doc = fh.read()
-    missing = [name for name in _declared_symbols() if f"fn {name}(" not in doc]
-    assert not missing, missing
+def test_rust_shim_binds_every_declared_symbol():
+    """shim/src/gpu/ffi.rs (the Rust `extern "C"` block a maintainer of the reference adds; generated from the header by
+    tools/gen_rust_ffi.py) names every entry point include/ministark.h declares, with the same number of arguments, and
+    is up to date with the header."""
+    import subprocess
+    import sys
+
+    with open(os.path.join(ROOT, "shim", "src", "gpu", "ffi.rs")) as fh:
+        rs = fh.read()
+    with open(os.path.join(ROOT, "include", "ministark.h")) as fh:
+        hdr = re.sub(r"/\*.*?\*/", " ", fh.read(), flags=re.S)
+    for name in _declared_symbols():
+        m = re.search(rf"pub fn {name}\(([^)]*)\)", rs)
+        assert m, f"{name} is not bound in shim/src/gpu/ffi.rs"
+        c = re.search(rf"\b{name}\s*\(([^;{{}}]*?)\)\s*;", hdr)
+        c_args = [a for a in c.group(1).split(",") if a.strip() and a.strip() != "void"]
+        r_args = [a for a in m.group(1).split(",") if a.strip()]
+        assert len(c_args) == len(r_args), (name, c_args, r_args)
+    # regenerating changes nothing
+    before = rs
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py")], stdout=subprocess.DEVNULL)
+    with open(os.path.join(ROOT, "shim", "src", "gpu", "ffi.rs")) as fh:
+        assert fh.read() == before, "shim/src/gpu/ffi.rs is stale: run python tools/gen_rust_ffi.py"
 
 
 def test_product_does_not_touch_the_oracle():

@@ -7,7 +7,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -5 gpurun_out/r02_b_bench_${N}gpu.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/r02_b_bench_${N}gpu.json"))
+s=open("gpurun_out/r02_b_bench_${N}gpu.json").read(); d=json.loads(s[s.index("{\"metric"):])
 print({k:d.get(k) for k in ("value","ms_per_step","prove_ms","n_gpus")})
 print(d.get("lde_weak")); print(d.get("e2e"))
 print(d["prove"]["stages_ms"]); print(d["prove"]["matches_oracle_digest"], d["prove"]["prove_samples_ms"])
