@@ -198,6 +198,12 @@ uint64_t ms_stark_proof_bound(int32_t field, const ms_stark_params* p, uint64_t 
  * Replaces: Stark::prove, src/starks.rs:59-169 (host transcript: src/fiatshamir.rs:48-64,96-116). */
 int32_t ms_stark_prove(ms_ctx* ctx, const ms_stark_params* p, const void* trace_rowmajor_host, uint64_t n, uint64_t w,
                        const void* constraint_matrix_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len);
+/* Affine transition constraints: row t of the AIR is f_{W+t} = sum_w M[t][w] f_w + c_t (constants_host: T canonical scalars, or
+ * NULL).  The reference proves such an AIR like any other (an affine combination still has at most N coefficients, so the
+ * `assert_eq!(rest, zero)` of src/starks.rs:119 holds); its closures are free to add a constant polynomial (src/air.rs:61). */
+int32_t ms_stark_prove_affine(ms_ctx* ctx, const ms_stark_params* p, const void* trace_rowmajor_host, uint64_t n, uint64_t w,
+                              const void* constraint_matrix_host, const void* constants_host, uint64_t t, uint8_t* proof_out,
+                              uint64_t* proof_len);
 /* Same with the trace already resident on the device (column-major W x N, stride n). */
 int32_t ms_stark_prove_device(ms_ctx* ctx, const ms_stark_params* p, const void* d_trace_colmajor, uint64_t n, uint64_t w,
                               const void* constraint_matrix_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len);

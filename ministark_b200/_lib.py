@@ -72,6 +72,7 @@ SIGNATURES = {
     "ms_stark_derive": (_i32, [_i32, C.POINTER(StarkParams), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "ms_stark_proof_bound": (_u64, [_i32, C.POINTER(StarkParams), _u64, _u64]),
     "ms_stark_prove": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "ms_stark_prove_affine": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_device": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
     "ms_stark_prove_hooked": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
     "ms_stark_verify": (_i32, [_vp, C.POINTER(StarkParams), _vp, _u64, _u64, _u64, _vp, _u64, _i32, C.POINTER(_i32), C.POINTER(_i32)]),

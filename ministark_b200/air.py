@@ -139,9 +139,29 @@ class TraceTable:
     def constrain_number(self) -> int:  # air.rs:123-125
         return self.width + len(self.transition_constrains)
 
+    def affine_form(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(M, c): closure t equals sum_w M[t][w] * trace_poly_w + c[t] (a constant polynomial).  Raises if a closure is
+        not affine in the trace polynomials: a product of two of them, or a multiplication by a non-constant polynomial,
+        reaches degree >= N and makes the reference panic at starks.rs:119."""
+        F, W = self.F, self.width
+        zero = DensePolynomial(F, [])
+        consts = np.zeros(len(self.transition_constrains), dtype=self.data.dtype)
+        shifted = []
+        for t, f in enumerate(self.transition_constrains):
+            c0 = f([zero] * W)
+            if len(c0.coeffs) > 1:
+                raise ValueError("transition constraint adds a non-constant polynomial: not expressible across the C ABI")
+            consts[t] = c0.coeffs[0] if c0.coeffs else 0
+            shifted.append(lambda P, f=f, c0=c0: f(P) - c0)
+        saved, self.transition_constrains = self.transition_constrains, shifted
+        try:
+            return self.linear_matrix(), consts
+        finally:
+            self.transition_constrains = saved
+
     def linear_matrix(self) -> np.ndarray:
         """T x W scalars such that closure t equals sum_w M[t][w] * trace_poly_w; raises if a closure is
-        not linear and homogeneous (such an AIR makes the reference panic at starks.rs:119)."""
+        not linear and homogeneous (use affine_form for constraints with an additive constant)."""
         F, W = self.F, self.width
         zero = DensePolynomial(F, [])
         one = DensePolynomial(F, [1])
@@ -149,7 +169,7 @@ class TraceTable:
         M = np.zeros((len(self.transition_constrains), W), dtype=self.data.dtype)
         for t, f in enumerate(self.transition_constrains):
             if f([zero] * W).coeffs:
-                raise ValueError("transition constraint has an additive term: not provable (starks.rs:119)")
+                raise ValueError("transition constraint has an additive term: use affine_form()")
             for j in range(W):
                 r = f([one if k == j else zero for k in range(W)])
                 if len(r.coeffs) > 1:
@@ -171,11 +191,13 @@ class TraceTable:
         ctx = ctx or Context(self.F.field_id)
         trace_cm = ctx.to_device(np.ascontiguousarray(self.data.T))
         polys = ctx.intt_columns(trace_cm)
-        m = self.linear_matrix()
+        m, consts = self.affine_form()
         if m.shape[0]:
             import torch
 
-            polys = torch.cat([polys, ctx.linear_constraints(polys, m)], dim=0)
+            cons = ctx.linear_constraints(polys, m)
+            cons[:, 0] = ctx.to_device((ctx.to_host(cons[:, 0]).astype(object) + consts.astype(object)) % self.F.p)  # + constant polynomial
+            polys = torch.cat([polys, cons], dim=0)
         return Constrains(self.width, m.shape[0], polys, ctx)
 
 

@@ -260,18 +260,26 @@ class Context:
 
     # ---------------------------------------------------------------- whole prover
     def stark_prove(self, params: StarkParams, trace_rm: np.ndarray, constraint_matrix: np.ndarray,
-                    capacity: Optional[int] = None) -> bytes:
+                    capacity: Optional[int] = None, constants: Optional[np.ndarray] = None) -> bytes:
+        """constants: optional T additive constants of affine constraints (ms_stark_prove_affine)"""
         trace_rm = np.ascontiguousarray(trace_rm, dtype=self.np_dtype)
         n, w = trace_rm.shape
         m = np.ascontiguousarray(constraint_matrix, dtype=self.np_dtype).reshape(-1, w)
+        cst = None if constants is None else np.ascontiguousarray(constants, dtype=self.np_dtype).reshape(m.shape[0])
         cap = C.c_uint64(capacity or (1 << 20))
         buf = np.empty(cap.value, dtype=np.uint8)
-        rc = self.lib.ms_stark_prove(self.h, C.byref(params), trace_rm.ctypes.data, n, w, m.ctypes.data, m.shape[0],
-                                     buf.ctypes.data, C.byref(cap))
+
+        def call():
+            if cst is None:
+                return self.lib.ms_stark_prove(self.h, C.byref(params), trace_rm.ctypes.data, n, w, m.ctypes.data, m.shape[0],
+                                               buf.ctypes.data, C.byref(cap))
+            return self.lib.ms_stark_prove_affine(self.h, C.byref(params), trace_rm.ctypes.data, n, w, m.ctypes.data, cst.ctypes.data,
+                                                  m.shape[0], buf.ctypes.data, C.byref(cap))
+
+        rc = call()
         if rc == 8:  # MS_ERR_BUFFER_TOO_SMALL: size written back
             buf = np.empty(cap.value, dtype=np.uint8)
-            rc = self.lib.ms_stark_prove(self.h, C.byref(params), trace_rm.ctypes.data, n, w, m.ctypes.data, m.shape[0],
-                                         buf.ctypes.data, C.byref(cap))
+            rc = call()
         self._check(rc)
         return buf[: cap.value].tobytes()
 

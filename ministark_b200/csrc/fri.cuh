@@ -246,24 +246,28 @@ int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stri
     out->path_len = path_len;
     out->ys.resize(3 * QF); out->found.resize(2 * QF); out->neigh.resize(4 * QF);
     out->paths.assign((size_t)2 * QF * path_len * 16, 0);
-    Scratch d_idx(c), d_ys(c), d_found(c), d_neigh_idx(c), d_neigh(c), d_paths(c);
+    // device buffers laid out so that each host round trip is one staged copy: [ys | found] and [neigh | paths]
+    Scratch d_idx(c), d_res(c), d_neigh_idx(c), d_np(c);
+    const size_t ys_bytes = 3 * QF * sizeof(E), found_bytes = 2 * QF * 8;
+    const size_t neigh_bytes = 4 * QF * sizeof(E), paths_bytes = out->paths.size() * 4;
     MS_TRY(d_idx.alloc(3 * QF * 8));
-    MS_TRY(d_ys.alloc(3 * QF * sizeof(E)));
-    MS_TRY(stage_from_host(c, i12.data(), i12.size() * 8, d_idx.p));
-    MS_TRY(stage_from_host(c, i3.data(), i3.size() * 8, d_idx.as<unsigned long long>() + 2 * QF));
-    k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys.as<E>());
+    MS_TRY(d_res.alloc(ys_bytes + found_bytes));
+    E* d_ys = d_res.as<E>();
+    unsigned long long* d_found = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(d_res.p) + ys_bytes);
+    std::vector<unsigned long long> idx3(3 * QF);
+    memcpy(idx3.data(), i12.data(), 2 * QF * 8);
+    memcpy(idx3.data() + 2 * QF, i3.data(), QF * 8);
+    MS_TRY(stage_from_host(c, idx3.data(), idx3.size() * 8, d_idx.p));
+    k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys);
     MS_LAUNCH_CHECK(c);
-    k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(d_next_cw, next_stride, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys.as<E>() + 2 * QF);
+    k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(d_next_cw, next_stride, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys + 2 * QF);
     MS_LAUNCH_CHECK(c);
-    MS_TRY(d_found.alloc(2 * QF * 8));
-    MS_CUDA(c, cudaMemsetAsync(d_found.p, 0xff, 2 * QF * 8, c->stream));
-    k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(d_prev_cw, prev_stride, nd, d_ys.as<E>(), (int)(2 * QF), d_found.as<unsigned long long>());
+    MS_CUDA(c, cudaMemsetAsync(d_found, 0xff, found_bytes, c->stream));
+    k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(d_prev_cw, prev_stride, nd, d_ys, (int)(2 * QF), d_found);
     MS_LAUNCH_CHECK(c);
     // small results go through mapped pinned memory, not the copy engine: a D2H copy here would queue behind the
     // previous rounds' multi-MB quotient downloads and serialise the query loop with the download
-    const size_t ys_bytes = 3 * QF * sizeof(E), found_bytes = 2 * QF * 8;
-    MS_TRY(stage_to_host(c, 0, d_ys.p, ys_bytes));
-    MS_TRY(stage_to_host(c, ys_bytes, d_found.p, found_bytes));
+    MS_TRY(stage_to_host(c, 0, d_res.p, ys_bytes + found_bytes));
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(out->ys.data(), c->hstage, ys_bytes);
     memcpy(out->found.data(), c->hstage + ys_bytes, found_bytes);
@@ -272,22 +276,22 @@ int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stri
     std::vector<unsigned long long> nidx(4 * QF);
     for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = out->found[k] & ~1ULL; nidx[2 * k + 1] = out->found[k] | 1ULL; }
     MS_TRY(d_neigh_idx.alloc(nidx.size() * 8));
-    MS_TRY(d_neigh.alloc(4 * QF * sizeof(E)));
-    MS_TRY(d_paths.alloc((size_t)2 * QF * (path_len ? path_len : 1) * 64));
+    MS_TRY(d_np.alloc(neigh_bytes + (paths_bytes ? paths_bytes : 64)));
+    E* d_neigh = d_np.as<E>();
+    uint32_t* d_paths = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_np.p) + neigh_bytes);
     MS_TRY(stage_from_host(c, nidx.data(), nidx.size() * 8, d_neigh_idx.p));
-    k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh.as<E>());
+    k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh);
     MS_LAUNCH_CHECK(c);
     if (path_len) {
         int total = (int)(2 * QF) * path_len * 16;
         if (sharded && sharded->world > 1)
             k_gather_paths_sharded<<<(total + 255) / 256, 256, 0, c->stream>>>(sharded->arenas, sharded->arena_off, sharded->world, sharded->top, nd / 2,
-                                                                              path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
+                                                                              path_len, d_found, (int)(2 * QF), d_paths);
         else
-            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_found.as<unsigned long long>(), (int)(2 * QF), d_paths.as<uint32_t>());
+            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_found, (int)(2 * QF), d_paths);
         MS_LAUNCH_CHECK(c);
-        MS_TRY(stage_to_host(c, 4 * QF * sizeof(E), d_paths.p, out->paths.size() * 4));
     }
-    MS_TRY(stage_to_host(c, 0, d_neigh.p, 4 * QF * sizeof(E)));
+    MS_TRY(stage_to_host(c, 0, d_np.p, neigh_bytes + paths_bytes));
     return MS_OK;  // the caller synchronises the stream, then calls fri_query_lookups_finish
 }
 template <class F>

@@ -384,6 +384,13 @@ int32_t ms_stark_prove(ms_ctx* c, const ms_stark_params* p, const void* trace_rm
     return FIELD_DISPATCH(c, CALL);
 #undef CALL
 }
+int32_t ms_stark_prove_affine(ms_ctx* c, const ms_stark_params* p, const void* trace_rm_host, uint64_t n, uint64_t w, const void* cmat_host,
+                              const void* cconst_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
+    if (!c->prover) c->prover = new ms::ProverState();
+#define CALL(F) stark_prove<F>(c, c->prover, *p, trace_rm_host, nullptr, n, w, (const F::T*)cmat_host, t, proof_out, proof_len, nullptr, 0, (const F::T*)cconst_host)
+    return FIELD_DISPATCH(c, CALL);
+#undef CALL
+}
 int32_t ms_stark_prove_device(ms_ctx* c, const ms_stark_params* p, const void* d_trace_cm, uint64_t n, uint64_t w,
                               const void* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len) {
     if (!c->prover) c->prover = new ms::ProverState();

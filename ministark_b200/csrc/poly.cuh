@@ -89,6 +89,35 @@ int linear_constraints_gather(Ctx* c, const typename F::T* const* d_cols, uint64
     return MS_OK;
 }
 
+// Additive constants of affine constraints (f_{W+t} = sum_w M[t][w] f_w + c_t): the constant polynomial c_t adds c_t to
+// coefficient 0 of the column -- or to every evaluation of it, when the column is built in evaluation space.
+template <class F>
+__global__ void k_add_consts(typename F::T* __restrict__ cols, uint64_t stride, uint64_t n, const typename F::T* __restrict__ consts, int t,
+                             int everywhere) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (everywhere ? n : 1)) return;
+    for (int r = 0; r < t; r++) {
+        const typename F::T cst = consts[r];
+        if (cst) cols[(uint64_t)r * stride + m] = F::add(cols[(uint64_t)r * stride + m], cst);
+    }
+}
+template <class F>
+int add_consts(Ctx* c, typename F::T* d_cols, uint64_t stride, uint64_t n, const typename F::T* consts_host, uint64_t t, bool everywhere) {
+    using T = typename F::T;
+    if (!consts_host || t == 0 || n == 0) return MS_OK;
+    std::vector<T> cs(t);
+    bool any = false;
+    for (uint64_t r = 0; r < t; r++) { cs[r] = (T)((uint64_t)consts_host[r] % (uint64_t)F::P); any = any || cs[r]; }
+    if (!any) return MS_OK;
+    Scratch dc(c);
+    MS_TRY(dc.alloc(t * sizeof(T)));
+    MS_TRY(stage_from_host(c, cs.data(), t * sizeof(T), dc.p));
+    const uint64_t work = everywhere ? n : 1;
+    k_add_consts<F><<<(unsigned)((work + 255) / 256), 256, 0, c->stream>>>(d_cols, stride, n, dc.as<T>(), (int)t, everywhere ? 1 : 0);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+
 // Sparse rows (at most 4 non-zero entries each: every AIR of the reference's tests, and the synthetic one): a row is a
 // short list of (column, scalar) pairs, +1 / -1 scalars cost an add / a sub instead of a product, and a thread handles two
 // consecutive elements with 16-byte loads.  Same values as k_linear_constraints (exact arithmetic).

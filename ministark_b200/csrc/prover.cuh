@@ -162,7 +162,7 @@ int sharded_tree_root(Ctx* c, Comm* cm, const typename F::T* d_data, uint64_t st
 template <class F>
 int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* trace_rm_host, const void* d_trace_cm_in,
                 uint64_t n, uint64_t w, const typename F::T* cmat_host, uint64_t t, uint8_t* proof_out, uint64_t* proof_len,
-                const ms_commit_hooks* hooks = nullptr, int32_t flags = 0) {
+                const ms_commit_hooks* hooks = nullptr, int32_t flags = 0, const typename F::T* cconst_host = nullptr) {
     using T = typename F::T;
     using E = Ext<F>;
     constexpr int D = F::D;
@@ -313,6 +313,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             MS_TRY(stage_from_host(c, cols.data(), w * sizeof(void*), ptab.p));
             if (sparse) MS_TRY(linear_sparse<F>(c, ptab.as<const T*>(), n, std::vector<SparseRow<F>>(srows.begin() + ta, srows.begin() + tb), my_cons_coef, n));
             else MS_TRY(linear_constraints_gather<F>(c, ptab.as<const T*>(), n, w, cmat_host + ta * w, nt, my_cons_coef, n));  // air.rs:130-134, own rows
+            MS_TRY(add_consts<F>(c, my_cons_coef, n, n, cconst_host ? cconst_host + ta : nullptr, nt, false));
         }
         tm.end();
     } else {
@@ -328,6 +329,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         } else {
             MS_TRY(linear_constraints<F>(c, coeffs.as<T>(), n, n, w, cmat_host, t, coeffs.as<T>() + w * n, n));  // air.rs:130-134
         }
+        MS_TRY(add_consts<F>(c, coeffs.as<T>() + w * n, n, n, cconst_host, t, false));
         tm.end();
     }
     if (hooks && hooks->lde_commit) {
@@ -352,6 +354,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             MS_TRY(etab.alloc(w * sizeof(void*)));
             MS_TRY(stage_from_host(c, cols.data(), w * sizeof(void*), etab.p));
             MS_TRY(linear_sparse<F>(c, etab.as<const T*>(), L, std::vector<SparseRow<F>>(srows.begin() + ta, srows.begin() + tb), my_lde + nw * L, L));
+            MS_TRY(add_consts<F>(c, my_lde + nw * L, L, L, cconst_host ? cconst_host + ta : nullptr, nt, true));
         } else if (!lde_by_linearity) {
             MS_TRY(lde_batch<F>(c, my_cons_coef, n, nt, ilog2(n), ilog2(B), shift, false, my_lde + nw * L, L));
         }
@@ -390,6 +393,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             Scratch etab(c);
             MS_TRY(column_table<F>(c, lde.as<T>(), L, w, &etab));
             MS_TRY(linear_sparse<F>(c, etab.as<const T*>(), L, srows, lde.as<T>() + w * L, L));               // constraint columns, pointwise
+            MS_TRY(add_consts<F>(c, lde.as<T>() + w * L, L, L, cconst_host, t, true));
         } else {
             MS_TRY(lde_batch<F>(c, coeffs.as<T>(), n, C, ilog2(n), ilog2(B), shift, false, lde.as<T>(), L));  // starks.rs:87-91
         }

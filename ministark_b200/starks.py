@@ -113,8 +113,9 @@ class Stark:
     def prove(self, air, witness) -> StarkProof:
         """Stark::prove (starks.rs:59-169)."""
         trace = air.trace(witness)
-        raw = self.ctx.stark_prove(self.config.params, trace.data, trace.linear_matrix(),
-                                   capacity=self.proof_bound(trace.length, trace.constrain_number()))
+        matrix, consts = trace.affine_form()
+        raw = self.ctx.stark_prove(self.config.params, trace.data, matrix, capacity=self.proof_bound(trace.length, trace.constrain_number()),
+                                   constants=consts if consts.any() else None)
         return StarkProof.from_bytes(raw)
 
     def proof_bound(self, n: int, cols: int) -> int:

@@ -41,9 +41,10 @@ def synth_linear_matrix(field: int, n: int, w: int) -> np.ndarray:
 class SynthAir:
     """pyref-compatible AIR over a given row-major trace and linear constraint matrix."""
 
-    def __init__(self, pyref, field: int, trace_rm: np.ndarray, matrix: np.ndarray, steps: int):
+    def __init__(self, pyref, field: int, trace_rm: np.ndarray, matrix: np.ndarray, steps: int, constants=None):
         self.R, self.F = pyref, pyref.FIELDS[field]
         self.trace_rm, self.matrix, self.steps = trace_rm, matrix, steps
+        self.constants = [0] * len(matrix) if constants is None else [int(c) for c in constants]  # affine closures: + c_t
 
     def trace(self, _witness=None):
         R, F = self.R, self.F
@@ -51,11 +52,11 @@ class SynthAir:
         t = R.TraceTable(F, self.steps, w, padding=0)
         assert t.length == n
         t.data = [int(v) for v in self.trace_rm.reshape(-1)]
-        for row in self.matrix:
+        for row, cst in zip(self.matrix, self.constants):
             coef = [int(c) for c in row]
 
-            def f(P, coef=coef):
-                acc = []
+            def f(P, coef=coef, cst=cst):
+                acc = [cst % F.p] if cst % F.p else []
                 for c, poly in zip(coef, P):
                     if c:
                         acc = R.poly_add(F, acc, R.poly_scale(F, poly, c))

@@ -381,10 +381,10 @@ API u64 or_fri_query_quotient(int field, const u64 *poly, u64 n, u64 x1, u64 x2,
 
 /* Stark::prove (src/starks.rs:59-169).  trace_rm: row-major N x W canonical elements (uint64 for both fields),
  * cmat: T x W.  stage_ms (optional): 8 doubles, see OR_T_*.  Returns the proof length or a negative error. */
-API int64_t or_stark_prove(int field, const or_stark_params *p, const u64 *trace_rm, u64 N, u64 W, const u64 *cmat, u64 T,
-                           unsigned char *out, u64 cap, int threads, double *stage_ms) {
-    return field == 0 ? gl_stark_prove(p, trace_rm, N, W, cmat, T, out, cap, threads, stage_ms)
-                      : bb_stark_prove(p, trace_rm, N, W, cmat, T, out, cap, threads, stage_ms);
+API int64_t or_stark_prove(int field, const or_stark_params *p, const u64 *trace_rm, u64 N, u64 W, const u64 *cmat, const u64 *cconst,
+                           u64 T, unsigned char *out, u64 cap, int threads, double *stage_ms) {
+    return field == 0 ? gl_stark_prove(p, trace_rm, N, W, cmat, cconst, T, out, cap, threads, stage_ms)
+                      : bb_stark_prove(p, trace_rm, N, W, cmat, cconst, T, out, cap, threads, stage_ms);
 }
 /* upper bound of the proof dump for an n x cols problem (same formula as ms_stark_proof_bound) */
 API u64 or_stark_proof_bound(int field, const or_stark_params *p, u64 n, u64 cols) {
@@ -409,12 +409,12 @@ API int or_stark_verify(int field, const or_stark_params *p, const u64 *coeffs, 
     return field == 0 ? gl_stark_verify(p, coeffs, N, C, proof, len, strict, why) : bb_stark_verify(p, coeffs, N, C, proof, len, strict, why);
 }
 /* the Constrains object of TraceTable::derive_constrains (src/air.rs:127-144) for a linear AIR: [W + T][N] */
-API void or_derive_constrains(int field, const u64 *trace_rm, u64 N, u64 W, const u64 *cmat, u64 T, u64 *out_cm, int threads) {
+API void or_derive_constrains(int field, const u64 *trace_rm, u64 N, u64 W, const u64 *cmat, const u64 *cconst, u64 T, u64 *out_cm, int threads) {
     if (field == 0) {
         gl_intt_job a = {trace_rm, N, W, out_cm}; or_parallel_items(W, threads, gl_intt_item, &a);
-        gl_cons_job b = {NULL, N, W, T, cmat, out_cm}; or_parallel_items(T, threads, gl_cons_item, &b);
+        gl_cons_job b = {cconst, N, W, T, cmat, out_cm}; or_parallel_items(T, threads, gl_cons_item, &b);
     } else {
         bb_intt_job a = {trace_rm, N, W, out_cm}; or_parallel_items(W, threads, bb_intt_item, &a);
-        bb_cons_job b = {NULL, N, W, T, cmat, out_cm}; or_parallel_items(T, threads, bb_cons_item, &b);
+        bb_cons_job b = {cconst, N, W, T, cmat, out_cm}; or_parallel_items(T, threads, bb_cons_item, &b);
     }
 }

@@ -68,9 +68,9 @@ def lib():
             "or_set_leftover_mode": (None, [i32]),
             "or_stark_derive": (i32, [i32, vp, vp, vp, vp]),
             "or_transcript_squeeze_test": (C.c_int64, [i32, u64, u64, u64, vp, u64, vp]),
-            "or_stark_prove": (C.c_int64, [i32, vp, vp, u64, u64, vp, u64, vp, u64, i32, vp]),
+            "or_stark_prove": (C.c_int64, [i32, vp, vp, u64, u64, vp, vp, u64, vp, u64, i32, vp]),
             "or_stark_verify": (i32, [i32, vp, vp, u64, u64, vp, u64, i32, vp]),
-            "or_derive_constrains": (None, [i32, vp, u64, u64, vp, u64, vp, i32]),
+            "or_derive_constrains": (None, [i32, vp, u64, u64, vp, vp, u64, vp, i32]),
             "or_stark_proof_bound": (u64, [i32, vp, u64, u64]),
         }
         for name, (res, args) in sig.items():
@@ -255,18 +255,20 @@ def stark_derive(field: int, security_bits: int, blowup: int, steps: int):
 
 
 def stark_prove(field: int, security_bits: int, blowup: int, steps: int, trace_columns: int, trace_rm, matrix,
-                inner_children: int = 2, threads: int = 1, want_timings: bool = False):
-    """Stark::prove (starks.rs:59-169) in C: returns the canonical proof bytes (and the per-stage wall ms)."""
+                inner_children: int = 2, threads: int = 1, want_timings: bool = False, constants=None):
+    """Stark::prove (starks.rs:59-169) in C: returns the canonical proof bytes (and the per-stage wall ms).
+    constants: optional T additive constants (affine transition closures)."""
     t = _u64(trace_rm)
     N, W = t.shape
     m = _u64(matrix).reshape(-1, W) if np.size(matrix) else np.zeros((0, W), dtype=np.uint64)
+    cst = None if constants is None else _u64(constants).reshape(m.shape[0])
     p = StarkParams(security_bits, blowup, steps, trace_columns, inner_children)
     ms = (C.c_double * len(STAGES))()
     bound = lib().or_stark_proof_bound(field, C.byref(p), N, W + m.shape[0])
     if bound == 0:
         raise ValueError(PROVE_ERRORS[-1])
     buf = np.empty(bound, dtype=np.uint8)
-    got = lib().or_stark_prove(field, C.byref(p), _p(t), N, W, _p(m), m.shape[0], _p(buf), bound, threads, ms)
+    got = lib().or_stark_prove(field, C.byref(p), _p(t), N, W, _p(m), _p(cst) if cst is not None else None, m.shape[0], _p(buf), bound, threads, ms)
     if got < 0:
         raise ValueError(PROVE_ERRORS.get(got, f"or_stark_prove: {got}"))
     assert got <= bound
@@ -280,19 +282,20 @@ def stark_prove_into(field: int, params: "StarkParams", trace_rm, matrix, out: n
     N, W = t.shape
     m = _u64(matrix).reshape(-1, W)
     ms = (C.c_double * len(STAGES))()
-    got = lib().or_stark_prove(field, C.byref(params), _p(t), N, W, _p(m), m.shape[0], _p(out), out.size, threads, ms)
+    got = lib().or_stark_prove(field, C.byref(params), _p(t), N, W, _p(m), None, m.shape[0], _p(out), out.size, threads, ms)
     if got < 0:
         raise ValueError(PROVE_ERRORS.get(got, f"or_stark_prove: {got}"))
     return got, dict(zip(STAGES, ms))
 
 
-def derive_constrains(field: int, trace_rm, matrix, threads: int = 1) -> np.ndarray:
-    """TraceTable::derive_constrains (air.rs:127-144) for a linear AIR: [W + T, N] coefficient vectors."""
+def derive_constrains(field: int, trace_rm, matrix, threads: int = 1, constants=None) -> np.ndarray:
+    """TraceTable::derive_constrains (air.rs:127-144) for a linear (affine with `constants`) AIR: [W + T, N] coefficient vectors."""
     t = _u64(trace_rm)
     N, W = t.shape
     m = _u64(matrix).reshape(-1, W)
+    cst = None if constants is None else _u64(constants).reshape(m.shape[0])
     out = np.zeros((W + m.shape[0], N), dtype=np.uint64)
-    lib().or_derive_constrains(field, _p(t), N, W, _p(m), m.shape[0], _p(out), threads)
+    lib().or_derive_constrains(field, _p(t), N, W, _p(m), _p(cst) if cst is not None else None, m.shape[0], _p(out), threads)
     return out
 
 

@@ -100,6 +100,16 @@ def test_trace_table_mirror_matches_air_rs(pyref):
     p = F.p
     assert m.tolist() == [[t.omega, p - 1, 0], [p - 1, p - 1, 1]]
     assert t.constrain_number() == 5
+    # closures with an additive constant polynomial (an affine AIR: provable by the reference, an affine combination still
+    # has at most N coefficients): the host mirror separates the matrix from the constants
+    t.add_transition_constrain(lambda P: P[1].clone() * DensePolynomial(F, [3]) + DensePolynomial(F, [p - 4]))
+    with pytest.raises(ValueError):
+        t.linear_matrix()
+    m2, c2 = t.affine_form()
+    assert m2.tolist() == [[t.omega, p - 1, 0], [p - 1, p - 1, 1], [0, 3, 0]] and c2.tolist() == [0, 0, p - 4]
+    t.add_transition_constrain(lambda P: P[0].clone() * P[1].clone())  # a product: degree >= N, starks.rs:119 panics
+    with pytest.raises(ValueError):
+        t.affine_form()
 
 
 @pytest.mark.parametrize("name,steps", [("Goldilocks", 9), ("BabyBear", 7)])

@@ -397,6 +397,27 @@ def test_c_prover_equals_python_prover_on_synthetic_airs(field, log_n, w, blowup
     assert oracle.stark_verify(field, sec, blowup, n - 1, 2 * w, oracle.derive_constrains(field, tr, mat), got, inner_children=k) == (True, 0)
 
 
+@pytest.mark.parametrize("field", [GL, BB])
+def test_c_prover_affine_constraints(field, pyref, oracle):
+    """transition closures that add a constant polynomial (src/air.rs:61 allows any closure; an affine one still has at most
+    N coefficients, so src/starks.rs:119 holds): C restatement = Python restatement, and the verifier accepts"""
+    from tests.synth import SynthAir, synth_linear_matrix, synth_trace
+
+    R = pyref
+    F = R.FIELDS[field]
+    n, w = 32, 2
+    tr, mat = synth_trace(field, n, w), synth_linear_matrix(field, n, w)
+    cst = np.array([5, F.p - 3], dtype=np.uint64)
+    cfg = R.StarkConfig(F, 30, 4, n - 1, 2 * w)
+    air = SynthAir(R, field, tr, mat, n - 1, constants=cst)
+    want = R.serialize_proof(F, R.Stark(cfg).prove(air, None))
+    got = oracle.stark_prove(field, 30, 4, n - 1, 2 * w, tr, mat, constants=cst).tobytes()
+    assert got == want
+    assert got != oracle.stark_prove(field, 30, 4, n - 1, 2 * w, tr, mat).tobytes()
+    cons = oracle.derive_constrains(field, tr, mat, constants=cst)
+    assert oracle.stark_verify(field, 30, 4, n - 1, 2 * w, cons, got) == (True, 0)
+
+
 def test_c_prover_matches_the_committed_scale_goldens(oracle):
     """tests/golden/scale_proofs.json (made by make_golden.py from this same C prover) is reproducible: the two
     smallest shapes are re-proved here; the GPU tests compare the CUDA prover with all of them."""
