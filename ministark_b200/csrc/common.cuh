@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -46,9 +47,14 @@ struct Ctx {
     struct NttTables {  // last two-pass transform's inter-pass factor table and coset block twiddles (ntt.cuh lde_batch)
         void* ft = nullptr;
         void* tw = nullptr;
+        size_t ft_bytes = 0, tw_bytes = 0;
         int logN = -1, logB = 0, inverse = 0, tile = 0, field = -1;
         uint64_t shift = 0;
     } ntt_tables;
+    // Device workspace: blocks handed out by Scratch come from, and go back to, this per-context cache (see Scratch).
+    std::multimap<size_t, void*> block_cache;
+    size_t cached_bytes = 0, cache_misses = 0;
+    int dl_skip_rank0 = 0;  // sharded proof download: leave rank 0 out of the split from 4 ranks on (MINISTARK_DL_SKIP_RANK0)
     int lde_linearity = 1;  // prover: constraint columns of the LDE by linearity when the constraint matrix is sparse (prover.cuh)
     int ntt_log_tile = 13;  // log2 elements of an NTT tile (ntt.cuh NTT_LOG_TILE_PREF); MINISTARK_NTT_TILE=12 selects half tiles
 };
@@ -86,27 +92,69 @@ inline int fail(Ctx* c, int code, const char* fmt, ...) {
                             cudaGetErrorString(e__), __FILE__, __LINE__);                    \
     } while (0)
 
-// Stream-ordered temporary (cudaMallocAsync pool; release threshold is raised at ctx creation so
-// steady-state allocations never reach the driver).
+// Device temporaries.  Every kernel of a context runs on its one stream, so a block can be handed to its next user the
+// moment the previous one lets go of it (the stream orders the two uses): Scratch takes blocks from a per-context cache
+// (best fit within 25 %, sizes rounded to 512 B / 2 MiB) and returns them there, and cudaMalloc only runs the first time a
+// shape is seen.  (r01 used the driver's stream-ordered pool, cudaMallocAsync: its remapping of freed ranges between
+// differently sized requests cost up to hundreds of ms per proof whenever the allocation pattern changed -- 2^24 x 64 proofs
+// took 327 ms in a fresh process and 1044 ms after other shapes had run, profiles/r02_d_bench_1gpu.json.)
+// The copy stream only ever reads blocks that stay alive until the call that queued the copies has synchronised it.
+inline size_t block_round(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    return bytes < (1u << 20) ? (bytes + 511) & ~(size_t)511 : (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+}
+inline void block_cache_release(Ctx* c) {  // give everything back to the driver (ctx teardown, or out of memory)
+    for (auto& kv : c->block_cache) cudaFree(kv.second);
+    c->block_cache.clear();
+    c->cached_bytes = 0;
+}
+inline int block_alloc(Ctx* c, size_t bytes, void** p, size_t* got) {
+    const size_t want = block_round(bytes);
+    auto it = c->block_cache.lower_bound(want);
+    if (it != c->block_cache.end() && it->first <= want + want / 4) {
+        *p = it->second;
+        *got = it->first;
+        c->cached_bytes -= it->first;
+        c->block_cache.erase(it);
+        return MS_OK;
+    }
+    c->cache_misses++;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and try once more
+        cudaGetLastError();
+        cudaStreamSynchronize(c->stream);
+        block_cache_release(c);
+        e = cudaMalloc(p, want);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(c, MS_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    *got = want;
+    return MS_OK;
+}
+inline void block_free(Ctx* c, void* p, size_t size) {
+    if (!p) return;
+    c->block_cache.emplace(size, p);
+    c->cached_bytes += size;
+}
 struct Scratch {
     Ctx* c;
     void* p = nullptr;
+    size_t size = 0;
     Scratch(Ctx* ctx) : c(ctx) {}
     Scratch(const Scratch&) = delete;
     Scratch& operator=(const Scratch&) = delete;
-    Scratch(Scratch&& o) noexcept : c(o.c), p(o.p) { o.p = nullptr; }
+    Scratch(Scratch&& o) noexcept : c(o.c), p(o.p), size(o.size) { o.p = nullptr; }
     int alloc(size_t bytes) {
-        if (bytes == 0) bytes = 16;
-        cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return fail(c, MS_ERR_CUDA, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
-        }
-        return MS_OK;
+        release();
+        return block_alloc(c, bytes, &p, &size);
     }
-    ~Scratch() {
-        if (p) cudaFreeAsync(p, c->stream);
+    void release() {
+        if (p) block_free(c, p, size);
+        p = nullptr;
     }
+    ~Scratch() { release(); }
     template <class T>
     T* as() { return reinterpret_cast<T*>(p); }
 };

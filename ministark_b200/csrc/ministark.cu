@@ -131,6 +131,7 @@ int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out)
     ms_ctx* c = new ms_ctx();
     c->field = field;
     c->device = device;
+    if (const char* e = getenv("MINISTARK_DL_SKIP_RANK0")) c->dl_skip_rank0 = atoi(e) ? 1 : 0;
     if (const char* e = getenv("MINISTARK_LDE_LINEARITY")) c->lde_linearity = atoi(e) ? 1 : 0;
     if (const char* e = getenv("MINISTARK_NTT_TILE")) {
         const int v = atoi(e);
@@ -143,11 +144,6 @@ int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out)
         cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return MS_ERR_CUDA;
-    }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     *out = c;
     return MS_OK;
@@ -164,6 +160,7 @@ void ms_ctx_destroy(ms_ctx* c) {
             if (c->tw16_plain[i][a]) cudaFree(c->tw16_plain[i][a]);
     if (c->ntt_tables.ft) cudaFree(c->ntt_tables.ft);
     if (c->ntt_tables.tw) cudaFree(c->ntt_tables.tw);
+    block_cache_release(c);
     if (c->dec4) cudaFree(c->dec4);
     if (c->hstage) cudaFreeHost(c->hstage);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

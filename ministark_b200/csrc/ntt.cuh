@@ -1036,9 +1036,9 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     if (blocks1 && !plain && two) {
         // cached with the factor table below (same key)
         if (!tc_hit) {
-            if (tc.tw) cudaFreeAsync(tc.tw, c->stream);  // stream-ordered: earlier launches that read it are ahead of the free
+            block_free(c, tc.tw, tc.tw_bytes);  // same stream: earlier launches that read it are ahead of its next user
             tc.tw = nullptr;
-            MS_CUDA(c, cudaMallocAsync(&tc.tw, ((size_t)B << (pl.a + 1)) * sizeof(T), c->stream));
+            MS_TRY(block_alloc(c, ((size_t)B << (pl.a + 1)) * sizeof(T), &tc.tw, &tc.tw_bytes));
             TwRoots<F> roots{};
             for (int l = 0; l <= NTT_MAXLOG; l++) {
                 T g = (l <= F::TWO_ADICITY) ? root_of_unity<F>(l) : (T)1;
@@ -1068,10 +1068,10 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     const int lay1 = pl.logR1 + logB;  // low index bits (m1 offset, coset) of the intermediate layout
     if (two) {
         if (!tc_hit) {
-            if (tc.ft) cudaFreeAsync(tc.ft, c->stream);
+            block_free(c, tc.ft, tc.ft_bytes);
             tc.ft = nullptr;
             tc.logN = -1;
-            MS_CUDA(c, cudaMallocAsync(&tc.ft, ((size_t)N << logB) * sizeof(T), c->stream));
+            MS_TRY(block_alloc(c, ((size_t)N << logB) * sizeof(T), &tc.ft, &tc.ft_bytes));
             int chunk_log = pl.a < 6 ? pl.a : 6;
             uint64_t threads = (((uint64_t)1 << pl.b) << logB) * ((1ULL << pl.a) >> chunk_log);
             prof_begin(c, "k_build_ft");

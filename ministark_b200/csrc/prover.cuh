@@ -401,8 +401,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
         tm.begin("lde_commit");
         MS_TRY(merkle_commit<F>(c, lde.as<T>(), L, L, C, 1, lpn, kk, nullptr, lde_root));  // starks.rs:92-94
         tm.end();
-        cudaFreeAsync(lde.p, c->stream);  // the LDE tree is never opened by the reference
-        lde.p = nullptr;
+        lde.release();  // the LDE tree is never opened by the reference
     }
     TR(merlin.add_bytes(lde_root, 32));
     // ---- 1.3 mixing                                                                  starks.rs:108-119
@@ -569,10 +568,11 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     // ---- serialise the fixed part (field order of starks.rs:21-28)
     // sharded download: every rank computes the same offsets, rank 0 alone writes the fixed part
     uint64_t copy_seq = 0;
-    // Which rank downloads (and therefore computes) the seq-th quotient polynomial.  From 4 ranks on, rank 0 takes
-    // none: it is the only one that runs the look-ups and writes the fixed part, which is then the critical path.
+    // Which rank downloads (and therefore computes) the seq-th quotient polynomial: round robin over all ranks.  (r01 left
+    // rank 0 out from 4 ranks on, because its look-ups then queued behind its own downloads; they go through mapped memory
+    // now, and an even split shortens the tail every other rank adds.  c->dl_skip_rank0 restores the old split.)
     auto owns = [&](uint64_t seq) -> bool {
-        if (dl_world >= 4) return dl_rank != 0 && seq % (dl_world - 1) + 1 == dl_rank;
+        if (c->dl_skip_rank0 && dl_world >= 4) return dl_rank != 0 && seq % (dl_world - 1) + 1 == dl_rank;
         return seq % dl_world == dl_rank;
     };
     ProofWriter pw(proof_out, proof_out ? *proof_len : 0);
