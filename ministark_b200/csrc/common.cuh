@@ -54,6 +54,7 @@ struct Ctx {
     // Device workspace: blocks handed out by Scratch come from, and go back to, this per-context cache (see Scratch).
     std::multimap<size_t, void*> block_cache;
     size_t cached_bytes = 0, cache_misses = 0;
+    int dl_max_ranks = 0;   // sharded proof download: at most this many ranks take a share (0: all; MINISTARK_DL_MAX_RANKS)
     int dl_skip_rank0 = 0;  // sharded proof download: leave rank 0 out of the split from 4 ranks on (MINISTARK_DL_SKIP_RANK0)
     int lde_linearity = 1;  // prover: constraint columns of the LDE by linearity when the constraint matrix is sparse (prover.cuh)
     int ntt_log_tile = 13;  // log2 elements of an NTT tile (ntt.cuh NTT_LOG_TILE_PREF); MINISTARK_NTT_TILE=12 selects half tiles
@@ -172,7 +173,7 @@ inline void prof_end(Ctx* c) {
     cudaEventRecord(c->prof.back().b, c->stream);
 }
 
-constexpr size_t HSTAGE_OUT = 2u << 20, HSTAGE_TOTAL = 8u << 20;
+constexpr size_t HSTAGE_OUT = 6u << 20, HSTAGE_TOTAL = 12u << 20;
 __global__ void k_store_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];

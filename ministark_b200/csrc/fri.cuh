@@ -221,15 +221,43 @@ struct ShardedNodes {  // where a row-sharded tree's digests live (k_gather_path
     int world = 0;
     const uint32_t* top = nullptr;
 };
+// leaf neighbours of the found leaves, indices taken on the device: out[2m], out[2m+1] = codeword[found[m] & ~1], [found[m] | 1]
+// (a target that was not found reads index 0: the host reports MS_ERR_LEAF_NOT_FOUND from `found` itself)
 template <class F>
-int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stride, uint64_t nd, const uint32_t* d_prev_nodes,
-                      const typename F::T* d_next_cw, uint64_t next_stride, uint64_t next_domain, const uint64_t* betas, uint64_t QF,
-                      QueryLookups<F>* out, const ShardedNodes* sharded = nullptr) {
+__global__ void k_gather_neigh(const typename F::T* __restrict__ cw, uint64_t stride, uint64_t n, const unsigned long long* __restrict__ found,
+                               int nt, Ext<F>* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * nt) return;
+    unsigned long long f = found[k >> 1];
+    if (f >= n) f = 0;
+    const unsigned long long i = (k & 1) ? (f | 1ULL) : (f & ~1ULL);
+    Ext<F> v;
+#pragma unroll
+    for (int d = 0; d < F::D; d++) v.c[d] = cw[(uint64_t)d * stride + i];
+    out[k] = v;
+}
+__global__ void k_clamp_found(unsigned long long* found, int nt, unsigned long long n, const unsigned long long* __restrict__ raw) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nt) found[k] = raw[k] >= n ? 0 : raw[k];
+}
+
+// Bytes one round's look-up results take in the device result buffer / the staging buffer:
+// [ys 3q E | found 2q u64 | neigh 4q E | paths 2q * path_len * 64]
+template <class F>
+inline size_t fri_lookup_bytes(uint64_t nd, uint64_t QF) {
+    return 7 * QF * sizeof(Ext<F>) + 2 * QF * 8 + (size_t)2 * QF * (size_t)ilog2(nd / 2) * 64;
+}
+// Queue one round's look-ups on the stream, results into d_res (fri_lookup_bytes long); no host round trip: the
+// neighbour and path gathers take the found indices from device memory.  Host-side values (points, s2) go to `out`.
+template <class F>
+int fri_query_lookups_enqueue(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stride, uint64_t nd, const uint32_t* d_prev_nodes,
+                              const typename F::T* d_next_cw, uint64_t next_stride, uint64_t next_domain, const uint64_t* betas, uint64_t QF,
+                              QueryLookups<F>* out, const ShardedNodes* sharded, uint8_t* d_res) {
     using T = typename F::T;
     using E = Ext<F>;
     if (!is_pow2(nd) || nd < 2 || next_domain * 2 != nd) return fail(c, MS_ERR_BAD_SHAPE, "FRI query: domains %llu -> %llu", (unsigned long long)nd, (unsigned long long)next_domain);
     const T g_prev = root_of_unity<F>(ilog2(nd)), g_next = root_of_unity<F>(ilog2(next_domain));
-    std::vector<unsigned long long> i12(2 * QF), i3(QF);
+    std::vector<unsigned long long> idx3(3 * QF);
     out->x1.resize(QF); out->x2.resize(QF); out->x3.resize(QF); out->s2.resize(QF);
     for (uint64_t k = 0; k < QF; k++) {
         uint64_t beta = betas[k];
@@ -238,66 +266,72 @@ int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stri
         out->x2[k] = fpow<F>(g_prev, next_domain + beta);                            // fri.rs:149
         out->x3[k] = fpow<F>(g_next, beta);                                          // fri.rs:150
         out->s2[k] = F::mul(out->x1[k], out->x1[k]);
-        i12[2 * k] = beta % nd;
-        i12[2 * k + 1] = (next_domain + beta) % nd;
-        i3[k] = beta % next_domain;
+        idx3[2 * k] = beta % nd;
+        idx3[2 * k + 1] = (next_domain + beta) % nd;
+        idx3[2 * QF + k] = beta % next_domain;
     }
     const int path_len = ilog2(nd / 2);
     out->path_len = path_len;
-    out->ys.resize(3 * QF); out->found.resize(2 * QF); out->neigh.resize(4 * QF);
-    out->paths.assign((size_t)2 * QF * path_len * 16, 0);
-    // device buffers laid out so that each host round trip is one staged copy: [ys | found] and [neigh | paths]
-    Scratch d_idx(c), d_res(c), d_neigh_idx(c), d_np(c);
-    const size_t ys_bytes = 3 * QF * sizeof(E), found_bytes = 2 * QF * 8;
-    const size_t neigh_bytes = 4 * QF * sizeof(E), paths_bytes = out->paths.size() * 4;
+    E* d_ys = reinterpret_cast<E*>(d_res);
+    unsigned long long* d_found = reinterpret_cast<unsigned long long*>(d_res + 3 * QF * sizeof(E));
+    E* d_neigh = reinterpret_cast<E*>(d_res + 3 * QF * sizeof(E) + 2 * QF * 8);
+    uint32_t* d_paths = reinterpret_cast<uint32_t*>(d_res + 7 * QF * sizeof(E) + 2 * QF * 8);
+    Scratch d_idx(c), d_fc(c);
     MS_TRY(d_idx.alloc(3 * QF * 8));
-    MS_TRY(d_res.alloc(ys_bytes + found_bytes));
-    E* d_ys = d_res.as<E>();
-    unsigned long long* d_found = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(d_res.p) + ys_bytes);
-    std::vector<unsigned long long> idx3(3 * QF);
-    memcpy(idx3.data(), i12.data(), 2 * QF * 8);
-    memcpy(idx3.data() + 2 * QF, i3.data(), QF * 8);
+    MS_TRY(d_fc.alloc(2 * QF * 8));
     MS_TRY(stage_from_host(c, idx3.data(), idx3.size() * 8, d_idx.p));
+    // y1, y2 = prev.poly(x1), prev.poly(x2); y3 = next.poly(x3): evaluations at domain points are codeword entries (exact
+    // arithmetic), so they are gathered instead of re-evaluated (fri.rs:151-153)
     k_gather_ext<F><<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_idx.as<unsigned long long>(), (int)(2 * QF), d_ys);
     MS_LAUNCH_CHECK(c);
     k_gather_ext<F><<<(unsigned)((QF + 127) / 128), 128, 0, c->stream>>>(d_next_cw, next_stride, d_idx.as<unsigned long long>() + 2 * QF, (int)QF, d_ys + 2 * QF);
     MS_LAUNCH_CHECK(c);
-    MS_CUDA(c, cudaMemsetAsync(d_found, 0xff, found_bytes, c->stream));
+    // openings by value search: first leaf equal to y (merkle.rs:216-225), for y1 and y2 of each query
+    MS_CUDA(c, cudaMemsetAsync(d_found, 0xff, 2 * QF * 8, c->stream));
     k_find_first<F><<<(unsigned)((nd + 255) / 256), 256, 2 * QF * sizeof(E), c->stream>>>(d_prev_cw, prev_stride, nd, d_ys, (int)(2 * QF), d_found);
     MS_LAUNCH_CHECK(c);
-    // small results go through mapped pinned memory, not the copy engine: a D2H copy here would queue behind the
-    // previous rounds' multi-MB quotient downloads and serialise the query loop with the download
-    MS_TRY(stage_to_host(c, 0, d_res.p, ys_bytes + found_bytes));
-    MS_CUDA(c, cudaStreamSynchronize(c->stream));
-    memcpy(out->ys.data(), c->hstage, ys_bytes);
-    memcpy(out->found.data(), c->hstage + ys_bytes, found_bytes);
-    for (auto f : out->found)
-        if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
-    std::vector<unsigned long long> nidx(4 * QF);
-    for (uint64_t k = 0; k < 2 * QF; k++) { nidx[2 * k] = out->found[k] & ~1ULL; nidx[2 * k + 1] = out->found[k] | 1ULL; }
-    MS_TRY(d_neigh_idx.alloc(nidx.size() * 8));
-    MS_TRY(d_np.alloc(neigh_bytes + (paths_bytes ? paths_bytes : 64)));
-    E* d_neigh = d_np.as<E>();
-    uint32_t* d_paths = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_np.p) + neigh_bytes);
-    MS_TRY(stage_from_host(c, nidx.data(), nidx.size() * 8, d_neigh_idx.p));
-    k_gather_ext<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, d_neigh_idx.as<unsigned long long>(), (int)(4 * QF), d_neigh);
+    k_gather_neigh<F><<<(unsigned)((4 * QF + 127) / 128), 128, 0, c->stream>>>(d_prev_cw, prev_stride, nd, d_found, (int)(2 * QF), d_neigh);
     MS_LAUNCH_CHECK(c);
     if (path_len) {
+        k_clamp_found<<<(unsigned)((2 * QF + 127) / 128), 128, 0, c->stream>>>(d_fc.as<unsigned long long>(), (int)(2 * QF), nd, d_found);
+        MS_LAUNCH_CHECK(c);
         int total = (int)(2 * QF) * path_len * 16;
         if (sharded && sharded->world > 1)
             k_gather_paths_sharded<<<(total + 255) / 256, 256, 0, c->stream>>>(sharded->arenas, sharded->arena_off, sharded->world, sharded->top, nd / 2,
-                                                                              path_len, d_found, (int)(2 * QF), d_paths);
+                                                                              path_len, d_fc.as<unsigned long long>(), (int)(2 * QF), d_paths);
         else
-            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_found, (int)(2 * QF), d_paths);
+            k_gather_paths<<<(total + 255) / 256, 256, 0, c->stream>>>(d_prev_nodes, nd / 2, path_len, d_fc.as<unsigned long long>(), (int)(2 * QF), d_paths);
         MS_LAUNCH_CHECK(c);
     }
-    MS_TRY(stage_to_host(c, 0, d_np.p, neigh_bytes + paths_bytes));
-    return MS_OK;  // the caller synchronises the stream, then calls fri_query_lookups_finish
+    return MS_OK;
 }
+// the staged copy of a round's results (host memory) -> out; MS_ERR_LEAF_NOT_FOUND like generate_proof (merkle.rs:216-225)
 template <class F>
-void fri_query_lookups_finish(Ctx* c, uint64_t QF, QueryLookups<F>* out) {
-    memcpy(out->neigh.data(), c->hstage, 4 * QF * sizeof(Ext<F>));
-    if (out->path_len) memcpy(out->paths.data(), c->hstage + 4 * QF * sizeof(Ext<F>), out->paths.size() * 4);
+int fri_query_lookups_parse(Ctx* c, const uint8_t* h_res, uint64_t nd, uint64_t QF, QueryLookups<F>* out) {
+    using E = Ext<F>;
+    out->ys.resize(3 * QF); out->found.resize(2 * QF); out->neigh.resize(4 * QF);
+    out->paths.assign((size_t)2 * QF * out->path_len * 16, 0);
+    memcpy(out->ys.data(), h_res, 3 * QF * sizeof(E));
+    memcpy(out->found.data(), h_res + 3 * QF * sizeof(E), 2 * QF * 8);
+    memcpy(out->neigh.data(), h_res + 3 * QF * sizeof(E) + 2 * QF * 8, 4 * QF * sizeof(E));
+    if (out->path_len) memcpy(out->paths.data(), h_res + 7 * QF * sizeof(E) + 2 * QF * 8, out->paths.size() * 4);
+    for (auto f : out->found)
+        if (f >= nd) return fail(c, MS_ERR_LEAF_NOT_FOUND, "leaf is not included in the tree");
+    return MS_OK;
+}
+// one round, synchronously (the stage export ms_fri_query)
+template <class F>
+int fri_query_lookups(Ctx* c, const typename F::T* d_prev_cw, uint64_t prev_stride, uint64_t nd, const uint32_t* d_prev_nodes,
+                      const typename F::T* d_next_cw, uint64_t next_stride, uint64_t next_domain, const uint64_t* betas, uint64_t QF,
+                      QueryLookups<F>* out, const ShardedNodes* sharded = nullptr) {
+    const size_t bytes = fri_lookup_bytes<F>(nd, QF);
+    Scratch res(c);
+    MS_TRY(res.alloc(bytes));
+    MS_TRY(fri_query_lookups_enqueue<F>(c, d_prev_cw, prev_stride, nd, d_prev_nodes, d_next_cw, next_stride, next_domain, betas, QF, out, sharded,
+                                        res.as<uint8_t>()));
+    MS_TRY(stage_to_host(c, 0, res.p, bytes));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return fri_query_lookups_parse<F>(c, c->hstage, nd, QF, out);
 }
 
 }  // namespace ms

@@ -94,8 +94,6 @@ static int fri_query_export(Ctx* c, const void* d_prev_poly, uint64_t poly_strid
     QueryLookups<F> lk;
     MS_TRY(fri_query_lookups<F>(c, (const T*)d_prev_cw, prev_cw_stride, prev_domain, d_prev_nodes, (const T*)d_next_cw, next_cw_stride,
                                 prev_domain / 2, betas, q, &lk));
-    MS_CUDA(c, cudaStreamSynchronize(c->stream));
-    fri_query_lookups_finish<F>(c, q, &lk);
     if (points_host) {
         E* pts = reinterpret_cast<E*>(points_host);
         for (uint64_t k = 0; k < q; k++) {
@@ -131,6 +129,7 @@ int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out)
     ms_ctx* c = new ms_ctx();
     c->field = field;
     c->device = device;
+    if (const char* e = getenv("MINISTARK_DL_MAX_RANKS")) c->dl_max_ranks = atoi(e);
     if (const char* e = getenv("MINISTARK_DL_SKIP_RANK0")) c->dl_skip_rank0 = atoi(e) ? 1 : 0;
     if (const char* e = getenv("MINISTARK_LDE_LINEARITY")) c->lde_linearity = atoi(e) ? 1 : 0;
     if (const char* e = getenv("MINISTARK_NTT_TILE")) {

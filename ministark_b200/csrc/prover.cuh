@@ -192,7 +192,11 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     const bool dl_native = cm && (flags & MS_PROOF_SHARED) && (mask & MS_SHARD_DOWNLOAD);
     const bool dl_sharded = dl_hooks || dl_native;
     const uint64_t dl_rank = dl_hooks ? (uint64_t)hooks->download_rank : (dl_native ? (uint64_t)rank : 0);
-    const uint64_t dl_world = dl_hooks ? (uint64_t)hooks->download_world : (dl_native ? (uint64_t)G : 1);
+    uint64_t dl_world = dl_hooks ? (uint64_t)hooks->download_world : (dl_native ? (uint64_t)G : 1);
+    // the shared host buffer sits behind one memory system: more than a handful of GPUs writing into it at once get less
+    // aggregate bandwidth than four do (profiles/r02_e_*): cap the number of downloading ranks (ranks beyond it compute nothing)
+    if (dl_native && c->dl_max_ranks > 0 && dl_world > (uint64_t)c->dl_max_ranks) dl_world = (uint64_t)c->dl_max_ranks;
+    const bool dl_idle = dl_native && (uint64_t)rank >= dl_world;  // this rank takes no share
     // ranks whose proof bytes nobody reads still run every stage that feeds the transcript (lock step) but compute
     // and download no quotient polynomials
     const bool replica_only = !dl_sharded && ((hooks && hooks->replica_only) || (cm && rank != 0 && !(flags & MS_PROOF_ALL_RANKS)));
@@ -572,6 +576,7 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     // rank 0 out from 4 ranks on, because its look-ups then queued behind its own downloads; they go through mapped memory
     // now, and an even split shortens the tail every other rank adds.  c->dl_skip_rank0 restores the old split.)
     auto owns = [&](uint64_t seq) -> bool {
+        if (dl_idle) return false;
         if (c->dl_skip_rank0 && dl_world >= 4) return dl_rank != 0 && seq % (dl_world - 1) + 1 == dl_rank;
         return seq % dl_world == dl_rank;
     };
@@ -591,49 +596,77 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
     pw.u64(Q);
     for (uint64_t q = 0; q < Q; q++) ser_ext<F>(pw, opens[q * (C + 1) + C]);
     pw.u64(R - 1);
-    struct PendingCopy { uint64_t at; const void* src; size_t bytes; };
-    std::vector<PendingCopy> copies;
+    // The query phase in two batches (r02; r01 made two host round trips per round, 46 per proof, each of them queued behind
+    // the multi-MB quotient downloads of the rounds before):
+    //   1. look-ups of ALL rounds (gathers, value search, neighbours, paths: the found indices never leave the device),
+    //      staged to the host in one copy, one event;
+    //   2. quotient kernels and their downloads of all rounds, queued without a host round trip: the offsets in the dump
+    //      only depend on sizes, so they are known before any value is;
+    // the host serialises the fixed part while the quotients stream out.
     cudaEvent_t dl[2] = {nullptr, nullptr};  // first / last proof-download copy on the copy stream (timing only)
+    cudaEvent_t ev_lk = nullptr;
     // every exit path below (errors included) waits for the downloads already queued into proof_out and frees the events
     struct CopyGuard {
         Ctx* c;
         cudaEvent_t* dl;
+        cudaEvent_t* lk;
         ~CopyGuard() {
             cudaStreamSynchronize(c->copy_stream);
             for (int i = 0; i < 2; i++)
                 if (dl[i]) { cudaEventDestroy(dl[i]); dl[i] = nullptr; }
+            if (*lk) { cudaEventDestroy(*lk); *lk = nullptr; }
         }
-    } copy_guard{c, dl};
+    } copy_guard{c, dl, &ev_lk};
     uint64_t dl_bytes = 0;
-    double q_host[4] = {0, 0, 0, 0};  // wall ms: look-ups + value search | neighbours, paths, quotients | serialise | enqueue copies
+    double q_host[4] = {0, 0, 0, 0};  // wall ms: queue look-ups | queue quotients + copies | wait for the look-ups | serialise
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_q = now_ms();
+    const bool lookups = !pw.mute;
+    const uint64_t E_ = sizeof(E);
+    // ---- 1. look-ups of every round
+    std::vector<QueryLookups<F>> lks(R ? R - 1 : 0);
+    std::vector<size_t> lk_off(R, 0);
+    size_t lk_total = 0;
     for (uint64_t i = 0; i + 1 < R; i++) {
-        double t_q = now_ms();
-        FriRoundDev<F>& prev = rounds[i];
-        FriRoundDev<F>& nxt = rounds[i + 1];
-        const uint64_t nd = prev.domain;
-        // A rank that only contributes quotient polynomials to a shared proof buffer (pw.mute) needs none of the
-        // look-ups: they feed the fixed part, which rank 0 writes (sizes are data independent, so the offsets agree).
-        const bool lookups = !pw.mute;
-        QueryLookups<F> lk;
-        if (lookups) {
-            MS_TRY(fri_query_lookups<F>(c, prev.cw, prev.domain, nd, prev.nodes, nxt.cw, nxt.domain, nxt.domain, betas.data(), QF, &lk, &prev.sh));
-            q_host[0] += now_ms() - t_q; t_q = now_ms();
-        } else {
+        lk_off[i] = lk_total;
+        lk_total += fri_lookup_bytes<F>(rounds[i].domain, QF);
+    }
+    Scratch d_lk(c);
+    if (lookups && lk_total) {
+        if (lk_total > HSTAGE_OUT) return fail(c, MS_ERR_UNSUPPORTED, "query look-ups need %zu staged bytes (limit %zu)", lk_total, (size_t)HSTAGE_OUT);
+        MS_TRY(d_lk.alloc(lk_total));
+        for (uint64_t i = 0; i + 1 < R; i++) {
+            FriRoundDev<F>& prev = rounds[i];
+            FriRoundDev<F>& nxt = rounds[i + 1];
+            MS_TRY(fri_query_lookups_enqueue<F>(c, prev.cw, prev.domain, prev.domain, prev.nodes, nxt.cw, nxt.domain, nxt.domain, betas.data(), QF,
+                                                &lks[i], &prev.sh, d_lk.as<uint8_t>() + lk_off[i]));
+        }
+        MS_TRY(stage_to_host(c, 0, d_lk.p, lk_total));
+        MS_CUDA(c, cudaEventCreateWithFlags(&ev_lk, cudaEventDisableTiming));
+        MS_CUDA(c, cudaEventRecord(ev_lk, c->stream));
+    } else {
+        for (uint64_t i = 0; i + 1 < R; i++) {  // ranks that only contribute quotients: the scan multipliers x1^2
+            const uint64_t nd = rounds[i].domain;
             const T g_prev = root_of_unity<F>(ilog2(nd));
-            lk.s2.resize(QF);
-            lk.path_len = ilog2(nd / 2);
+            lks[i].s2.resize(QF);
+            lks[i].path_len = ilog2(nd / 2);
             for (uint64_t k = 0; k < QF; k++) {
                 uint64_t beta = betas[k];
                 if (beta > nd) beta %= nd;
                 const T x1 = fpow<F>(g_prev, beta);
-                lk.s2[k] = F::mul(x1, x1);
+                lks[i].s2[k] = F::mul(x1, x1);
             }
         }
-        const std::vector<T>& s2 = lk.s2;
-        const int path_len = lk.path_len;
-        // quotients (fri.rs:157-167): only the ones this rank downloads (all of them unless the download is sharded)
-        const uint64_t nq = prev.len >= 3 ? prev.len - 2 : 0;
+    }
+    q_host[0] = now_ms() - t_q; t_q = now_ms();
+    // ---- 2. quotients (fri.rs:157-167): only the ones this rank downloads (all of them unless the download is sharded),
+    // each to its final offset in the dump
+    uint64_t pos = pw.pos;
+    for (uint64_t i = 0; i + 1 < R; i++) {
+        FriRoundDev<F>& prev = rounds[i];
+        const uint64_t nq = prev.len >= 3 ? prev.len - 2 : 0, path_len = (uint64_t)lks[i].path_len;
+        const uint64_t per_q = 6 * E_ + 2 * (8 + 2 * E_ + 8 + path_len * (8 + 64)) + 8 + nq * E_;
+        pos += 8;  // the round's Vec length
         T* d_quot = nullptr;
         std::vector<int> slot(QF, -1);  // query k's quotient is the slot[k]-th polynomial of d_quot
         if (nq) {
@@ -641,71 +674,78 @@ int stark_prove(Ctx* c, ProverState* ps, const ms_stark_params& p, const void* t
             for (uint64_t k = 0; k < QF; k++)
                 if (owns(copy_seq + k) && !replica_only) {
                     slot[k] = (int)s2_own.size();
-                    s2_own.push_back(s2[k]);
+                    s2_own.push_back(lks[i].s2[k]);
                 }
+            copy_seq += QF;
             if (!s2_own.empty()) {
                 MS_TRY(dev_alloc(s2_own.size() * nq * sizeof(E), (void**)&d_quot));
-                MS_TRY(fri_query_quotients<F>(c, prev.poly, prev.npad, prev.len, s2_own.data(), (uint32_t)s2_own.size(), d_quot));
+                // large rounds go query by query, so that the first download starts after one polynomial's scan instead of
+                // after the whole round's (the copy engine is the bottleneck of this phase: keep it fed from the start)
+                const size_t step = nq * E_ >= (8u << 20) ? 1 : s2_own.size();
+                std::vector<uint64_t> owner_of_slot(s2_own.size());
+                for (uint64_t k = 0; k < QF; k++)
+                    if (slot[k] >= 0) owner_of_slot[slot[k]] = k;
+                for (size_t s0 = 0; s0 < s2_own.size(); s0 += step) {
+                    const size_t cnt = std::min(step, s2_own.size() - s0);
+                    MS_TRY(fri_query_quotients<F>(c, prev.poly, prev.npad, prev.len, s2_own.data() + s0, (uint32_t)cnt, d_quot + s0 * nq * D));
+                    MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
+                    MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
+                    if (!dl[0]) {
+                        cudaEventCreate(&dl[0]);
+                        cudaEventCreate(&dl[1]);
+                        cudaEventRecord(dl[0], c->copy_stream);
+                    }
+                    for (size_t sl = s0; sl < s0 + cnt; sl++) {
+                        const uint64_t at = pos + owner_of_slot[sl] * per_q + (per_q - nq * E_);
+                        MS_CUDA(c, cudaMemcpyAsync(proof_out + at, d_quot + sl * nq * D, nq * E_, cudaMemcpyDeviceToHost, c->copy_stream));
+                        dl_bytes += nq * E_;
+                    }
+                }
             }
         }
-        MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (lookups) fri_query_lookups_finish<F>(c, QF, &lk);
-        else { lk.ys.assign(3 * QF, ext_zero<F>()); lk.neigh.assign(4 * QF, ext_zero<F>()); lk.paths.assign((size_t)2 * QF * path_len * 16, 0); lk.x1.assign(QF, 0); lk.x2.assign(QF, 0); lk.x3.assign(QF, 0); }
-        const std::vector<E>&ys = lk.ys, &neigh = lk.neigh;
-        const std::vector<uint32_t>& paths = lk.paths;
-        const std::vector<T>&x1 = lk.x1, &x2 = lk.x2, &x3 = lk.x3;
-        q_host[1] += now_ms() - t_q; t_q = now_ms();
-        // ---- serialise this round (fri.rs:18-22, merkle.rs:293-298)
+        pos += QF * per_q;
+    }
+    q_host[1] = now_ms() - t_q; t_q = now_ms();
+    // ---- 3. the look-up results, then the dump's fixed bytes (fri.rs:18-22, merkle.rs:293-298)
+    if (ev_lk) {
+        MS_CUDA(c, cudaEventSynchronize(ev_lk));
+        for (uint64_t i = 0; i + 1 < R; i++) MS_TRY(fri_query_lookups_parse<F>(c, c->hstage + lk_off[i], rounds[i].domain, QF, &lks[i]));
+    }
+    q_host[2] = now_ms() - t_q; t_q = now_ms();
+    for (uint64_t i = 0; i + 1 < R; i++) {
+        QueryLookups<F>& lk = lks[i];
+        const uint64_t nq = rounds[i].len >= 3 ? rounds[i].len - 2 : 0;
+        const int path_len = lk.path_len;
+        if (!lookups) { lk.ys.assign(3 * QF, ext_zero<F>()); lk.neigh.assign(4 * QF, ext_zero<F>()); lk.paths.assign((size_t)2 * QF * path_len * 16, 0); lk.x1.assign(QF, 0); lk.x2.assign(QF, 0); lk.x3.assign(QF, 0); }
         pw.u64(QF);
         for (uint64_t k = 0; k < QF; k++) {
-            E pts[6] = {ext_from_base<F>(x1[k]), ys[2 * k], ext_from_base<F>(x2[k]), ys[2 * k + 1], ext_from_base<F>(x3[k]), ys[2 * QF + k]};
+            E pts[6] = {ext_from_base<F>(lk.x1[k]), lk.ys[2 * k], ext_from_base<F>(lk.x2[k]), lk.ys[2 * k + 1], ext_from_base<F>(lk.x3[k]), lk.ys[2 * QF + k]};
             for (int e = 0; e < 6; e++) ser_ext<F>(pw, pts[e]);
             for (int which = 0; which < 2; which++) {
                 uint64_t m = 2 * k + which;
                 pw.u64(2);
-                ser_ext<F>(pw, neigh[2 * m]);
-                ser_ext<F>(pw, neigh[2 * m + 1]);
+                ser_ext<F>(pw, lk.neigh[2 * m]);
+                ser_ext<F>(pw, lk.neigh[2 * m + 1]);
                 pw.u64(path_len);
                 for (int l = 0; l < path_len; l++) {
                     pw.u64(2);
-                    for (int s = 0; s < 2; s++) {
+                    for (int sb = 0; sb < 2; sb++) {
                         uint8_t dg[32];
-                        digest_words_to_bytes(&paths[((size_t)m * path_len + l) * 16 + s * 8], dg);
+                        digest_words_to_bytes(&lk.paths[((size_t)m * path_len + l) * 16 + sb * 8], dg);
                         pw.bytes(dg, 32);
                     }
                 }
             }
             pw.u64(nq);
-            if (nq) {
-                const uint64_t at = pw.reserve(nq * sizeof(E));
-                if (slot[k] >= 0) copies.push_back({at, d_quot + (size_t)slot[k] * nq * D, (size_t)(nq * sizeof(E))});
-            }
+            if (nq) pw.reserve(nq * sizeof(E));  // filled by the download queued above
         }
-        if (nq) copy_seq += QF;
-        q_host[2] += now_ms() - t_q; t_q = now_ms();
-        // The quotient polynomials are ~all of the proof bytes (fri.rs:167): start this round's download on
-        // the copy stream now, so it overlaps the next rounds' kernels and host work (the proof buffer was
-        // checked against the size bound up front, so every offset is in range).
-        if (!copies.empty()) {
-            MS_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
-            MS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
-            if (!dl[0]) {
-                cudaEventCreate(&dl[0]);
-                cudaEventCreate(&dl[1]);
-                cudaEventRecord(dl[0], c->copy_stream);
-            }
-            for (auto& cp : copies) {
-                MS_CUDA(c, cudaMemcpyAsync(proof_out + cp.at, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-                dl_bytes += cp.bytes;
-            }
-            copies.clear();
-        }
-        q_host[3] += now_ms() - t_q;
     }
-    ps->timings.emplace_back("(query host: look-ups + search)", (float)q_host[0]);
-    ps->timings.emplace_back("(query host: paths + quotients)", (float)q_host[1]);
-    ps->timings.emplace_back("(query host: serialise)", (float)q_host[2]);
-    ps->timings.emplace_back("(query host: enqueue copies)", (float)q_host[3]);
+    if (pw.pos != pos) return fail(c, MS_ERR_UNSUPPORTED, "proof layout mismatch (%llu vs %llu)", (unsigned long long)pw.pos, (unsigned long long)pos);
+    q_host[3] = now_ms() - t_q;
+    ps->timings.emplace_back("(query host: queue look-ups)", (float)q_host[0]);
+    ps->timings.emplace_back("(query host: queue quotients + copies)", (float)q_host[1]);
+    ps->timings.emplace_back("(query host: wait for look-ups)", (float)q_host[2]);
+    ps->timings.emplace_back("(query host: serialise)", (float)q_host[3]);
     if (dl[0]) cudaEventRecord(dl[1], c->copy_stream);
     MS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     if (dl[0]) {

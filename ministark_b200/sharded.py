@@ -31,6 +31,7 @@ CPU-only gloo tests, an oracle-backed stand-in defined under tests/.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -354,6 +355,22 @@ class ShardedCommitter:
         return _lib.CommitHooks(None, self._cb[0], self._cb[1], 1 if replica_only else 0, download[0], download[1])
 
 
+def _touch_interleaved(buf, nbytes: int) -> None:
+    """first-touch the buffer under MPOL_INTERLEAVE so that its pages alternate between the host's NUMA nodes (all ranks'
+    downloads then spread over every memory controller instead of landing on rank 0's node)"""
+    import glob
+
+    nodes = len(glob.glob("/sys/devices/system/node/node[0-9]*")) or 1
+    libc = C.CDLL(None, use_errno=True)
+    mask = C.c_ulong((1 << nodes) - 1)
+    MPOL_DEFAULT, MPOL_INTERLEAVE, SYS_set_mempolicy = 0, 3, 238  # x86_64
+    ok = nodes > 1 and libc.syscall(SYS_set_mempolicy, MPOL_INTERLEAVE, C.byref(mask), C.c_ulong(nodes + 1)) == 0
+    a = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+    a[::4096] = 0
+    if ok:
+        libc.syscall(SYS_set_mempolicy, MPOL_DEFAULT, None, C.c_ulong(0))
+
+
 class SharedProofBuffer:
     """One host buffer for the proof, visible to every rank of a node (POSIX shared memory) and page-locked in
     every process, so that each rank can download its share of the quotient polynomials over its own PCIe
@@ -369,6 +386,8 @@ class SharedProofBuffer:
         if rank == 0:
             self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
             names[0] = self.shm.name
+            if os.environ.get("MINISTARK_SHM_INTERLEAVE", "0") != "0":
+                _touch_interleaved(self.shm.buf, nbytes)  # spread the pages over the NUMA nodes before anyone pins them
         src = dist.get_global_rank(group, 0) if group is not None else 0
         dist.broadcast_object_list(names, src=src, group=group)
         if rank != 0:
