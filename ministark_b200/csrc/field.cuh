@@ -83,7 +83,22 @@ struct BB {
     }
     static MS_HD T sub(T a, T b) { return a >= b ? a - b : a + P - b; }
     static MS_HD T neg(T a) { return a ? P - a : 0; }
-    static MS_HD T mul(T a, T b) { return (T)(((uint64_t)a * b) % P); }
+    // Montgomery reduction t 2^-32 mod p for t < p 2^32, result canonical (-p^-1 mod 2^32 = 2013265919)
+    static MS_HD T redc(uint64_t t) {
+        const uint32_t m = (uint32_t)t * 2013265919u;
+        const uint32_t u = (uint32_t)(((uint64_t)m * P + t) >> 32), v = u - P;  // u in [0, 2p)
+        return u < v ? u : v;
+    }
+    static MS_HD T mul(T a, T b) {
+#ifdef __CUDA_ARCH__
+        // canonical in, canonical out without the 64-bit division: REDC(REDC(a b) 2^64) -- two IMAD.WIDE pairs
+        // (8 instructions) against 13 with two IMAD.HI chains for "% P"
+        constexpr uint32_t R2 = (uint32_t)((((uint64_t)1 << 32) % P) * (((uint64_t)1 << 32) % P) % P);
+        return redc((uint64_t)redc((uint64_t)a * b) * R2);
+#else
+        return (T)(((uint64_t)a * b) % P);
+#endif
+    }
     static MS_HD T mul_small(T a, uint32_t c) { return mul(a, c % P); }
 };
 
