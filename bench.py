@@ -444,10 +444,11 @@ def run_ours(args):
                     torch.cuda.synchronize()
                     if i > 0:
                         ts.append((time.perf_counter() - t0) * 1e3)
-                entry = {"prove_ms": float(np.mean(ts)), "proof_bytes": pl, "stages_ms": {k: round(v, 2) for k, v in ctx.last_timings()}}
+                entry = {"prove_ms": float(np.mean(ts)), "proof_bytes": pl, "proof_sha256": hashlib.sha256(pbuf[:pl].tobytes()).hexdigest(),
+                         "stages_ms": {k: round(v, 2) for k, v in ctx.last_timings()}}
                 if logn == 20:
                     g3 = golden_digest("config3a_gl_2^20x16_b8")
-                    entry["matches_oracle_digest"] = bool(g3 and args.security_bits == 100 and hashlib.sha256(pbuf[:pl].tobytes()).hexdigest() == g3["proof_sha256"])
+                    entry["matches_oracle_digest"] = bool(g3 and args.security_bits == 100 and entry["proof_sha256"] == g3["proof_sha256"])
                 cfgs[name] = entry
                 del pbuf, tcm
             except Exception as e:  # noqa: BLE001  (e.g. out of memory on a smaller part): report, do not fail the bench
@@ -457,6 +458,36 @@ def run_ours(args):
         extras["baseline_configs_note"] = ("configs 3 and 5 as written (4-ary / 8-ary trees over 2^23 / 2^26 rows) are rejected like the "
                                            "reference's MerkleTree::new would ('Tree is not full!', merkle.rs:93-104); these are the same "
                                            "sizes with the binary trees StarkConfig::new builds (starks.rs:283-302)")
+
+    # ---- extras (N > 1): BASELINE config 5a (2^24 x 64, blowup 4) as ONE sharded proof (north_star: reported at 1/2/4/8 GPUs)
+    if world > 1 and not args.no_extras:
+        from ministark_b200.sharded import SharedProofBuffer
+        from ministark_b200.synth import synth_linear_matrix
+
+        del out, coeffs, all_coeffs
+        torch.cuda.empty_cache()
+        nn, w_ = 1 << 24, 32
+        pr = StarkParams(args.security_bits, 4, nn - 1, 2 * w_, 2)
+        bd = int(ctx.lib.ms_stark_proof_bound(GL, pr, nn, 2 * w_))
+        sh5 = SharedProofBuffer(ctx, bd, dist)
+        tcm = ctx.trace_synth(nn, w_, seed=SEED + 3)  # the same trace as the N = 1 line's 5a entry
+        mm = synth_linear_matrix(GL, nn, w_)
+        ts, pl = [], 0
+        for i in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            pl = ctx.stark_prove_multi(pr, tcm, mm, sh5.array, shared=True)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            if i > 0:
+                ts.append(dt * 1e3)
+        extras["baseline_configs"] = {"5a: 2^24 x 64, blowup 4, binary trees": {
+            "prove_ms": float(np.mean(ts)), "prove_samples_ms": [round(v, 1) for v in ts], "proof_bytes": pl, "n_gpus": world,
+            "proof_sha256": hashlib.sha256(sh5.array[:pl].tobytes()).hexdigest() if rank == 0 else None,
+            "stages_ms": {k: round(v, 2) for k, v in ctx.last_timings()},
+            "what": "one proof sharded over the ranks (ms_stark_prove_multi), trace generated on the device, max over ranks"}}
+        del tcm
+        sh5.close()
 
     # ---- CPU baseline (rank 0, N = 1): the C restatement, single thread like the reference ---------------------
     cpu = None

@@ -44,13 +44,19 @@ struct Ctx {
     // multi-GPU: the communicator this context is a rank of (nullptr: single GPU) and which stages shard
     Comm* comm = nullptr;
     int shard_mask = MS_SHARD_ALL;
-    struct NttTables {  // last two-pass transform's inter-pass factor table and coset block twiddles (ntt.cuh lde_batch)
+    struct NttTables {  // a two-pass transform's inter-pass factor table and coset block twiddles (ntt.cuh lde_batch)
         void* ft = nullptr;
         void* tw = nullptr;
         size_t ft_bytes = 0, tw_bytes = 0;
         int logN = -1, logB = 0, inverse = 0, tile = 0, field = -1;
         uint64_t shift = 0;
-    } ntt_tables;
+        uint64_t stamp = 0;  // last use (least recently used entries leave first)
+    };
+    // One entry per (n, blowup, shift, direction, tile size): a proof runs the trace iNTT, the LDE and one codeword transform
+    // per FRI round, each with its own tables, and the FRI ones (shift 1) are the same for every proof of a shape.
+    std::vector<NttTables> ntt_tables;
+    uint64_t ntt_tables_clock = 0;
+    size_t ntt_tables_budget = (size_t)4 << 30;  // bytes kept across calls (MINISTARK_NTT_TABLE_MB); one entry always stays
     // Device workspace: blocks handed out by Scratch come from, and go back to, this per-context cache (see Scratch).
     std::multimap<size_t, void*> block_cache;
     size_t cached_bytes = 0, cache_misses = 0;

@@ -29,31 +29,26 @@ __global__ void k_build_dec4(uint32_t* tab) {
 }
 
 // The message of one leaf group is assembled as big-endian 32-bit words in a per-thread buffer in
-// shared memory (word i of thread t at buf[i*LEAF_THREADS + t]: conflict free).  `wp` points at the
-// word that holds the `fill` (0..3) pending bytes, left aligned, zeros below; everything beyond it is
-// don't-care.  Appending a string = one funnel shift per word + one store per word at compile-time
-// offsets from `wp`; no byte stores, no per-byte address arithmetic.
+// shared memory (word i of thread t at buf[i*LEAF_THREADS + t]: conflict free).  `pos` counts the bytes
+// in the buffer: pos >> 2 complete words, then the word with the pos & 3 pending bytes (left aligned,
+// zeros below); everything beyond it is don't-care.  Appending a string = one funnel shift per word +
+// one store per word at compile-time offsets from that word; no byte stores, no per-byte address
+// arithmetic, and one 32-bit counter to maintain per token (the message length is 64 * blocks + pos).
 struct LeafStream {
     uint32_t* base;  // word 0 of this thread
-    uint32_t* wp;    // word with the pending bytes
-    uint32_t wr;     // complete words in the buffer
-    uint32_t fill;   // pending bytes in *wp
-    uint64_t total;  // message bytes so far
+    uint32_t pos;    // bytes in the buffer
 
     // X[0..NW): the string, left aligned, big-endian characters, zero padded; len <= 4*NW bytes
     template <int NW>
     __device__ __forceinline__ void append(const uint32_t (&X)[NW], uint32_t len) {
-        const uint32_t sh = 8u * fill;
+        uint32_t* wp = base + (pos >> 2) * LEAF_THREADS;
+        const uint32_t sh = 8u * (pos & 3u);
         const uint32_t part = *wp;
         wp[0] = part | (X[0] >> sh);
 #pragma unroll
         for (int k = 1; k < NW; k++) wp[k * LEAF_THREADS] = __funnelshift_r(X[k], X[k - 1], sh);
         wp[NW * LEAF_THREADS] = __funnelshift_r(0u, X[NW - 1], sh);
-        const uint32_t t = fill + len;
-        wp += (t >> 2) * LEAF_THREADS;
-        wr += t >> 2;
-        fill = t & 3u;
-        total += len;
+        pos += len;
     }
 };
 
@@ -143,87 +138,93 @@ k_leaf_hash(const typename F::T* __restrict__ data, uint64_t stride, uint64_t wi
     const bool live = g < n_groups;
     LeafStream st;
     st.base = buf + threadIdx.x;
-    st.wp = st.base;
-    st.wr = 0;
-    st.fill = 0;
-    st.total = 0;
+    st.pos = 0;
     st.base[0] = 0;
     uint32_t h[8];
     sha256_init(h);
-    const uint64_t ntok = live ? lpn * Tokens<DEG>::PER_ELEM : 0;
-    uint64_t tok = 0;
-    uint64_t f = g * lpn;          // flat index of the current element
-    uint64_t row = live ? f / width : 0, col = live ? f % width : 0;
+    // 32-bit token / column counters (the host side bounds lpn and width); only the row index is 64-bit
+    const uint32_t ntok = live ? (uint32_t)lpn * Tokens<DEG>::PER_ELEM : 0;
+    const uint32_t wid = (uint32_t)width;
+    uint32_t tok = 0;
+    const uint64_t f = g * lpn;    // flat index of the first element
+    uint64_t row = live ? f / width : 0;
+    uint32_t col = live ? (uint32_t)(f % width) : 0;
     int sub = 0;                   // token index inside the current element
     bool padded = !live, finished = !live;
-    uint32_t end_words = 0;        // words of the padded message tail (16 or 32) once padded
+    uint32_t nblk = 0;             // blocks compressed so far
+    // base-field leaves out of one matrix: the element pointer walks along the row (+stride per column, back to the
+    // next row's first column at the end) instead of being recomputed from (col, row) per element
+    const T* ep = data + (uint64_t)col * stride + row;
+    const int64_t ep_wrap = 1 - (int64_t)((width - 1) * stride);
     // base-field leaves: the element of the next token is loaded one token ahead, so that the load
     // (HBM, or NVLink in GATHER mode) is in flight during the decimal conversion / compression
     // (GATHER only: measured 3 % slower on local HBM, where 32 resident warps already hide the latency)
     T ahead = (GATHER && DEG == 1 && ntok) ? load(col, row) : (T)0;
     while (__any_sync(0xffffffffu, !finished)) {
         // ---- fill: append tokens until a full block is pending
-        while (st.wr < 16 && tok < ntok) {
+        while (st.pos < 64 && tok < ntok) {
             if (DEG == 1 && GATHER) {
                 const T v = ahead;
                 if (tok + 1 < ntok) {
-                    const bool wrap = col + 1 == width;
+                    const bool wrap = col + 1 == wid;
                     ahead = load(wrap ? 0 : col + 1, wrap ? row + 1 : row);
                 }
                 put_decimal(st, (uint64_t)v, zero_empty, dec4);
             } else if (DEG == 1) {
-                put_decimal(st, (uint64_t)load(col, row), zero_empty, dec4);
+                put_decimal(st, (uint64_t)*ep, zero_empty, dec4);
+                ep += (col + 1 == wid) ? ep_wrap : (int64_t)stride;
             } else if (DEG == 2) {
                 switch (sub) {
                     case 0: put_lit(st, "QuadExtField("); break;
-                    case 1: put_decimal(st, (uint64_t)load((col * 2 + 0), row), zero_empty, dec4); break;
+                    case 1: put_decimal(st, (uint64_t)load(((uint64_t)col * 2 + 0), row), zero_empty, dec4); break;
                     case 2: put_lit(st, " + "); break;
-                    case 3: put_decimal(st, (uint64_t)load((col * 2 + 1), row), zero_empty, dec4); break;
+                    case 3: put_decimal(st, (uint64_t)load(((uint64_t)col * 2 + 1), row), zero_empty, dec4); break;
                     default: put_lit(st, " * u)"); break;
                 }
             } else {
                 switch (sub) {
                     case 0: put_lit(st, "QuadExtField("); break;
                     case 1: put_lit(st, "QuadExtField("); break;
-                    case 2: put_decimal(st, (uint64_t)load((col * 4 + 0), row), zero_empty, dec4); break;
+                    case 2: put_decimal(st, (uint64_t)load(((uint64_t)col * 4 + 0), row), zero_empty, dec4); break;
                     case 3: put_lit(st, " + "); break;
-                    case 4: put_decimal(st, (uint64_t)load((col * 4 + 1), row), zero_empty, dec4); break;
+                    case 4: put_decimal(st, (uint64_t)load(((uint64_t)col * 4 + 1), row), zero_empty, dec4); break;
                     case 5: put_lit(st, " * u) + "); break;
                     case 6: put_lit(st, "QuadExtField("); break;
-                    case 7: put_decimal(st, (uint64_t)load((col * 4 + 2), row), zero_empty, dec4); break;
+                    case 7: put_decimal(st, (uint64_t)load(((uint64_t)col * 4 + 2), row), zero_empty, dec4); break;
                     case 8: put_lit(st, " + "); break;
-                    case 9: put_decimal(st, (uint64_t)load((col * 4 + 3), row), zero_empty, dec4); break;
+                    case 9: put_decimal(st, (uint64_t)load(((uint64_t)col * 4 + 3), row), zero_empty, dec4); break;
                     default: put_lit(st, " * u) * u)"); break;
                 }
             }
             tok++;
             if (++sub == Tokens<DEG>::PER_ELEM) {
                 sub = 0;
-                if (++col == width) { col = 0; row++; }
+                if (++col == wid) { col = 0; row++; }
             }
         }
         // ---- padding once the message is complete (FIPS 180-4 5.1.1)
-        if (!padded && st.wr < 16 && tok >= ntok) {
-            const uint64_t bits = st.total * 8;
+        if (!padded && st.pos < 64 && tok >= ntok) {
+            const uint64_t bits = ((uint64_t)nblk * 64 + st.pos) * 8;
             const uint32_t one[1] = {0x80000000u};
             st.append<1>(one, 1);
-            const uint32_t nw = st.wr + (st.fill ? 1u : 0u);  // words holding data
-            end_words = nw <= 14 ? 16u : 32u;
+            const uint32_t nw = (st.pos + 3u) >> 2;  // words holding data
+            const uint32_t end_words = nw <= 14 ? 16u : 32u;
             for (uint32_t i = nw; i < end_words - 2; i++) st.base[i * LEAF_THREADS] = 0;
             st.base[(end_words - 2) * LEAF_THREADS] = (uint32_t)(bits >> 32);
             st.base[(end_words - 1) * LEAF_THREADS] = (uint32_t)bits;
-            st.wr = end_words;
+            st.pos = 4u * end_words;
             padded = true;
         }
         // ---- compress one pending block and slide the rest of the buffer down
-        if (!finished && st.wr >= 16) {
+        if (!finished && st.pos >= 64) {
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) w[i] = st.base[i * LEAF_THREADS];
             sha256_compress(h, w);
-            st.wr -= 16;
+            st.pos -= 64;
+            nblk++;
             if (padded) {
-                if (st.wr == 0) finished = true;
+                if (st.pos == 0) finished = true;
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; i++) st.base[i * LEAF_THREADS] = st.base[(i + 16) * LEAF_THREADS];
@@ -232,7 +233,6 @@ k_leaf_hash(const typename F::T* __restrict__ data, uint64_t stride, uint64_t wi
                 // at most 6 complete words plus the partial one were beyond the block
 #pragma unroll
                 for (int i = 0; i < 7; i++) st.base[i * LEAF_THREADS] = st.base[(i + 16) * LEAF_THREADS];
-                st.wp -= 16 * LEAF_THREADS;
             }
         }
     }
@@ -402,6 +402,8 @@ template <class F>
 int merkle_leaf_level(Ctx* c, const typename F::T* d_data, uint64_t stride, uint64_t width, int deg, uint64_t lpn, uint64_t n1,
                       uint32_t* d_nodes, bool gather = false) {
     unsigned blocks = (unsigned)((n1 + LEAF_THREADS - 1) / LEAF_THREADS);
+    if (lpn > (1ULL << 27) || width >= (1ULL << 32))  // the leaf kernel counts tokens and columns in 32 bits
+        return fail(c, MS_ERR_UNSUPPORTED, "leaf groups of %llu elements / rows of %llu columns are beyond the leaf kernel's counters", (unsigned long long)lpn, (unsigned long long)width);
     prof_begin(c, "k_leaf_hash");
     MS_TRY(ensure_dec4(c));
     if (gather) {

@@ -132,6 +132,7 @@ int32_t ms_ctx_create(int32_t field, int32_t device, void* stream, ms_ctx** out)
     if (const char* e = getenv("MINISTARK_DL_MAX_RANKS")) c->dl_max_ranks = atoi(e);
     if (const char* e = getenv("MINISTARK_DL_SKIP_RANK0")) c->dl_skip_rank0 = atoi(e) ? 1 : 0;
     if (const char* e = getenv("MINISTARK_LDE_LINEARITY")) c->lde_linearity = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("MINISTARK_NTT_TABLE_MB")) c->ntt_tables_budget = (size_t)atoll(e) << 20;
     if (const char* e = getenv("MINISTARK_NTT_TILE")) {
         const int v = atoi(e);
         if (v == NTT_LOG_TILE_PREF || v == NTT_LOG_TILE_PREF - 1) c->ntt_log_tile = v;
@@ -157,8 +158,10 @@ void ms_ctx_destroy(ms_ctx* c) {
     for (int i = 0; i < 2; i++)
         for (int a = 0; a < 16; a++)
             if (c->tw16_plain[i][a]) cudaFree(c->tw16_plain[i][a]);
-    if (c->ntt_tables.ft) cudaFree(c->ntt_tables.ft);
-    if (c->ntt_tables.tw) cudaFree(c->ntt_tables.tw);
+    for (auto& t : c->ntt_tables) {
+        if (t.ft) cudaFree(t.ft);
+        if (t.tw) cudaFree(t.tw);
+    }
     block_cache_release(c);
     if (c->dec4) cudaFree(c->dec4);
     if (c->hstage) cudaFreeHost(c->hstage);

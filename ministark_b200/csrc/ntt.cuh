@@ -975,6 +975,32 @@ int launch_tile(Ctx* c, const NttTile<F>& g, const char* name) {
     return MS_OK;
 }
 
+// Cached tables of two-pass transforms (Ctx::ntt_tables): look-up by key, and a fresh entry after evicting the least
+// recently used ones beyond the byte budget.  Everything runs on the context's one stream, so a table handed back to the
+// block cache is only reused behind the launches that still read it.
+inline Ctx::NttTables* ntt_tables_find(Ctx* c, int logN, int logB, uint64_t shift, int inverse, int field) {
+    for (auto& t : c->ntt_tables)
+        if (t.ft && t.logN == logN && t.logB == logB && t.shift == shift && t.inverse == inverse && t.tile == c->ntt_log_tile && t.field == field) {
+            t.stamp = ++c->ntt_tables_clock;
+            return &t;
+        }
+    return nullptr;
+}
+inline Ctx::NttTables* ntt_tables_new(Ctx* c, size_t need_bytes) {
+    auto& v = c->ntt_tables;
+    auto total = [&] { size_t b = 0; for (auto& t : v) b += t.ft_bytes + t.tw_bytes; return b; };
+    while (!v.empty() && (v.size() >= 48 || total() + need_bytes > c->ntt_tables_budget)) {
+        size_t lru = 0;
+        for (size_t i = 1; i < v.size(); i++) if (v[i].stamp < v[lru].stamp) lru = i;
+        block_free(c, v[lru].ft, v[lru].ft_bytes);
+        block_free(c, v[lru].tw, v[lru].tw_bytes);
+        v.erase(v.begin() + lru);
+    }
+    v.emplace_back();
+    v.back().stamp = ++c->ntt_tables_clock;
+    return &v.back();
+}
+
 // See the header comment.  d_in and d_out must not alias.
 template <class F>
 int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t cols, int logN, int logB,
@@ -1014,9 +1040,11 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     // The coset block-twiddle table and the inter-pass factor table only depend on (n, blowup, shift, direction, tile size):
     // they are kept for the next call with the same key (the prover extends its columns in several calls per proof, a
     // benchmark repeats one call), built on this stream and only ever used on it.
-    Ctx::NttTables& tc = c->ntt_tables;
-    const bool tc_hit = tc.ft && tc.logN == logN && tc.logB == logB && tc.shift == (uint64_t)shift && tc.inverse == (inverse ? 1 : 0) &&
-                        tc.tile == c->ntt_log_tile && tc.field == F::ID;
+    Ctx::NttTables tc_none;
+    Ctx::NttTables* tcp = two ? ntt_tables_find(c, logN, logB, (uint64_t)shift, inverse ? 1 : 0, F::ID) : nullptr;
+    const bool tc_hit = tcp != nullptr;
+    if (two && !tc_hit) tcp = ntt_tables_new(c, (((size_t)N << logB) + ((size_t)B << (pl.a + 1))) * sizeof(T));
+    Ctx::NttTables& tc = tcp ? *tcp : tc_none;
     // geometry of the first pass decides which kernel runs it, and with it the twiddle-table format
     NttTile<F> g1{};
     g1.a = pl.a;
