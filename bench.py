@@ -469,6 +469,18 @@ def run_ours(args):
         nn, w_ = 1 << 24, 32
         pr = StarkParams(args.security_bits, 4, nn - 1, 2 * w_, 2)
         bd = int(ctx.lib.ms_stark_proof_bound(GL, pr, nn, 2 * w_))
+        room = [None]
+        if rank == 0:  # the shared proof buffer lives in /dev/shm: every rank takes the same decision
+            try:
+                st_ = os.statvfs("/dev/shm")
+                room[0] = st_.f_bavail * st_.f_frsize
+            except OSError:
+                room[0] = 0
+        dist.broadcast_object_list(room, src=0)
+        if room[0] < bd + (256 << 20):
+            extras["baseline_configs"] = {"5a: 2^24 x 64, blowup 4, binary trees": {"skipped": f"/dev/shm has {room[0] >> 20} MiB free, the proof buffer needs {bd >> 20} MiB"}}
+            nn = 0
+    if world > 1 and not args.no_extras and nn:
         sh5 = SharedProofBuffer(ctx, bd, dist)
         tcm = ctx.trace_synth(nn, w_, seed=SEED + 3)  # the same trace as the N = 1 line's 5a entry
         mm = synth_linear_matrix(GL, nn, w_)
