@@ -62,6 +62,33 @@ def test_coset_lde(field, log_n, blowup, cols, ctxs, oracle):
         assert (got_h == want).all()
 
 
+@pytest.mark.parametrize("budget_mb", ["0", "4096"])
+def test_ntt_table_cache_hits_misses_and_evictions(budget_mb, oracle, monkeypatch):
+    """Two-pass transforms keep their factor / twiddle tables per (n, blowup, shift, direction) in the context
+    (Ctx::ntt_tables): interleaved shapes, shifts and directions must give the oracle's values whether every call
+    rebuilds its tables (budget 0: each new entry evicts the last one) or finds them again."""
+    from ministark_b200 import Context
+
+    monkeypatch.setenv("MINISTARK_NTT_TABLE_MB", budget_mb)
+    ctx = Context(GL)
+    try:
+        cases = [(15, 4, 3), (16, 2, 5), (15, 4, 7), (15, 4, 3), (16, 2, 5), (15, 4, 3)]  # (log_n, blowup, shift)
+        want = {}
+        for rep, (log_n, blowup, shift) in enumerate(cases):
+            n = 1 << log_n
+            coeffs = rand_field(GL, (2, n), 900 + log_n)
+            key = (log_n, blowup, shift)
+            if key not in want:
+                want[key] = oracle.coset_lde(GL, coeffs, n * blowup, shift, threads=4)
+            got = ctx.to_host(ctx.coset_lde(ctx.to_device(coeffs), blowup, shift))
+            assert (got.T == want[key]).all(), (rep, key)
+            if rep in (1, 4):  # an inverse transform of the same size in between (its own tables)
+                trace = rand_field(GL, (n, 2), 950 + log_n)
+                assert (ctx.to_host(ctx.intt_columns(ctx.to_device(np.ascontiguousarray(trace.T)))) == oracle.trace_polys(GL, trace)).all()
+    finally:
+        ctx.close()
+
+
 def test_coset_lde_max_two_pass_size(ctxs, oracle):
     """2^22 coefficients x blowup 4 (the headline shape's per-column transform), one column."""
     ctx = ctxs[GL]
