@@ -881,16 +881,37 @@ inline bool ntt_plan(int logN, int logB, NttPlan* p, int T = NTT_LOG_TILE_PREF) 
     return true;
 }
 
+// The plan lde_batch uses: the context's tile size, except that a 4-byte field whose cosets would have to be split over
+// pass-1 tiles takes 2^14-element tiles instead (64 KB, the byte size of a Goldilocks tile): no split, no second read of the
+// input, and pass-2 runs of 16-32 contiguous bytes per point instead of 8 (BabyBear from 2^23 rows at blowup 4; the
+// transform stays in place: such plans have logR1 = 0).  *tile_log returns the tile size the plan was made for.
+template <class F>
+inline bool ntt_plan_for(int logN, int logB, int pref_tile, NttPlan* p, int* tile_log) {
+    *tile_log = pref_tile;
+    if (!ntt_plan(logN, logB, p, pref_tile)) return false;
+    if (sizeof(typename F::T) == 4 && pref_tile == NTT_LOG_TILE_PREF && p->cs1 > 0) {
+        NttPlan q;
+        if (ntt_plan(logN, logB, &q, NTT_LOG_TILE_PREF + 1)) {
+            *p = q;
+            *tile_log = NTT_LOG_TILE_PREF + 1;
+        }
+    }
+    return true;
+}
+
 // tile shapes with a compile-time specialisation
 // (A + BETA = 13: 8192-element tiles, 256 threads, 3 CTAs / SM; A + BETA = 12: 4096-element tiles, 128 threads, 6 CTAs / SM --
 // the same warps per SM in CTAs half the size: barriers couple fewer warps and load / compute phases of more CTAs interleave)
 #define MS_NTT_FIXED_SHAPES(X) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0) X(8, 4) X(9, 3) X(10, 2) X(11, 1) X(12, 0)
+// A + BETA = 14, 4-byte fields only (ntt_plan_for): the 64 KB tiles of large BabyBear transforms
+#define MS_NTT_FIXED_SHAPES_W4(X) X(11, 3) X(12, 2) X(13, 1)
 // does launch_tile run this tile through k_ntt_fixed (and, for Goldilocks, with block twiddles)?
 template <class F>
 inline bool tile_is_fixed(const NttTile<F>& g) {
     if (!(g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0))) return false;
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) return true;
     MS_NTT_FIXED_SHAPES(X)
+    if (sizeof(typename F::T) == 4) { MS_NTT_FIXED_SHAPES_W4(X) }
 #undef X
     return false;
 }
@@ -960,6 +981,7 @@ int launch_tile(Ctx* c, const NttTile<F>& g, const char* name) {
     if (tile_is_fixed<F>(g)) {
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) return launch_fixed<F, A_, B_>(c, g, name);
         MS_NTT_FIXED_SHAPES(X)
+        if constexpr (sizeof(T) == 4) { MS_NTT_FIXED_SHAPES_W4(X) }
 #undef X
     }
     const size_t smem = tile_rounds(g.a) > 1 ? (sizeof(T) << (g.a + g.beta)) : 0;
@@ -978,9 +1000,9 @@ int launch_tile(Ctx* c, const NttTile<F>& g, const char* name) {
 // Cached tables of two-pass transforms (Ctx::ntt_tables): look-up by key, and a fresh entry after evicting the least
 // recently used ones beyond the byte budget.  Everything runs on the context's one stream, so a table handed back to the
 // block cache is only reused behind the launches that still read it.
-inline Ctx::NttTables* ntt_tables_find(Ctx* c, int logN, int logB, uint64_t shift, int inverse, int field) {
+inline Ctx::NttTables* ntt_tables_find(Ctx* c, int logN, int logB, uint64_t shift, int inverse, int field, int tile_log) {
     for (auto& t : c->ntt_tables)
-        if (t.ft && t.logN == logN && t.logB == logB && t.shift == shift && t.inverse == inverse && t.tile == c->ntt_log_tile && t.field == field) {
+        if (t.ft && t.logN == logN && t.logB == logB && t.shift == shift && t.inverse == inverse && t.tile == tile_log && t.field == field) {
             t.stamp = ++c->ntt_tables_clock;
             return &t;
         }
@@ -1011,7 +1033,8 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     if (inverse && logB != 0) return fail(c, MS_ERR_UNSUPPORTED, "inverse transform with blowup");
     if (cols >= (1ULL << 20)) return fail(c, MS_ERR_UNSUPPORTED, "too many columns");
     NttPlan pl;
-    if (!ntt_plan(logN, logB, &pl, c->ntt_log_tile)) return fail(c, MS_ERR_UNSUPPORTED, "transform 2^%d x blowup 2^%d too large", logN, logB);
+    int tile_log = c->ntt_log_tile;
+    if (!ntt_plan_for<F>(logN, logB, c->ntt_log_tile, &pl, &tile_log)) return fail(c, MS_ERR_UNSUPPORTED, "transform 2^%d x blowup 2^%d too large", logN, logB);
     MS_TRY(ensure_wtab<F>(c, inverse ? 1 : 0));
     const T* wtab = reinterpret_cast<const T*>(c->wtab[inverse ? 1 : 0]);
     const int B = 1 << logB;
@@ -1041,7 +1064,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
     // they are kept for the next call with the same key (the prover extends its columns in several calls per proof, a
     // benchmark repeats one call), built on this stream and only ever used on it.
     Ctx::NttTables tc_none;
-    Ctx::NttTables* tcp = two ? ntt_tables_find(c, logN, logB, (uint64_t)shift, inverse ? 1 : 0, F::ID) : nullptr;
+    Ctx::NttTables* tcp = two ? ntt_tables_find(c, logN, logB, (uint64_t)shift, inverse ? 1 : 0, F::ID, tile_log) : nullptr;
     const bool tc_hit = tcp != nullptr;
     if (two && !tc_hit) tcp = ntt_tables_new(c, (((size_t)N << logB) + ((size_t)B << (pl.a + 1))) * sizeof(T));
     Ctx::NttTables& tc = tcp ? *tcp : tc_none;
@@ -1107,7 +1130,7 @@ int lde_batch(Ctx* c, const typename F::T* d_in, uint64_t in_stride, uint64_t co
                                                                                    logB, pl.logR1, chunk_log);
             prof_end(c);
             MS_LAUNCH_CHECK(c);
-            tc.logN = logN; tc.logB = logB; tc.shift = (uint64_t)shift; tc.inverse = inverse ? 1 : 0; tc.tile = c->ntt_log_tile; tc.field = F::ID;
+            tc.logN = logN; tc.logB = logB; tc.shift = (uint64_t)shift; tc.inverse = inverse ? 1 : 0; tc.tile = tile_log; tc.field = F::ID;
         }
         if (!inplace) MS_TRY(tmp.alloc(cols * ((size_t)N << logB) * sizeof(T)));
     }

@@ -58,6 +58,7 @@ static bool emu_is_fixed(const NttTile<F>& g) {
     if (!(g.mode == 0 || g.logR1 <= g.a - tile_round_size(g.a, 0))) return false;
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) return true;
     EMU_FIXED_SHAPES(X)
+    if (sizeof(typename F::T) == 4) { MS_NTT_FIXED_SHAPES_W4(X) }  // the 2^14-element tiles of large 4-byte transforms
 #undef X
     return false;
 }
@@ -68,6 +69,7 @@ static void run_any(const NttTile<F>& g) {
     if (emu_is_fixed<F>(g)) {
 #define X(A_, B_) if (g.a == A_ && g.beta == B_) { g_fixed_used++; return run_fixed<F, A_, B_>(g); }
         EMU_FIXED_SHAPES(X)
+        if constexpr (sizeof(typename F::T) == 4) { MS_NTT_FIXED_SHAPES_W4(X) }
 #undef X
     }
     run_tiles<F>(g, 64);
@@ -100,7 +102,8 @@ static std::vector<typename F::T> emu_lde(const std::vector<typename F::T>& in, 
                                           typename F::T shift, bool inverse, int force_a) {
     using T = typename F::T;
     NttPlan pl;
-    if (!ntt_plan(logN, logB, &pl, g_tile_log)) { printf("plan failed\n"); exit(2); }
+    int tile_log = 0;
+    if (!ntt_plan_for<F>(logN, logB, g_tile_log, &pl, &tile_log)) { printf("plan failed\n"); exit(2); }
     if (force_a >= 0) {  // exercise two-pass geometry on small sizes
         pl.a = force_a; pl.b = logN - force_a;
         pl.logR1 = 0; pl.cs1 = 0; pl.beta1 = logB; pl.beta2 = logB;
@@ -280,6 +283,9 @@ int main() {
     bad += check<BB>(12, 2, false, 7, 1);
     bad += check<GL>(23, 2, false, -1, 1);   // planner's own coset split: (12,1) + (11,2)
     bad += check<GL>(14, 0, true, -1, 1);
+    bad += check<BB>(23, 2, false, -1, 1);   // 4-byte field, cosets would split: 2^14-element tiles, (12,2) + (11,3)
+    bad += check<BB>(22, 3, false, -1, 1);   // (11,3) + (11,3)
+    bad += check<BB>(24, 2, false, -1, 1);   // (12,2) + (12,2)
     // half-size tiles (MINISTARK_NTT_TILE=12): 4096-element tiles, the headline shape becomes (11,1) + (11,1) with the cosets
     // split over two pass-1 tiles
     g_tile_log = NTT_LOG_TILE_PREF - 1;
