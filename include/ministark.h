@@ -103,7 +103,8 @@ int32_t ms_trace_recurrence(ms_ctx* ctx, const void* matrix_host, const void* ro
  * elements of `deg` coordinates each (deg = 1 base field, deg = D extension planes): leaf group g
  * hashes SHA256(concat(to_string(e))) of flat elements [g*lpn, (g+1)*lpn), inner nodes hash `k`
  * child digests, nodes in level order.  d_nodes (optional) receives all (k^levels-1)/(k-1)
- * digests (8 words each); root32 (optional, host) the root bytes.
+ * digests (8 words each); root32 (optional, host) the root bytes.  Limits of the leaf kernel's
+ * 32-bit counters: leafs_per_node <= 2^27, width < 2^32 (MS_ERR_UNSUPPORTED beyond).
  * Replaces: MerkleTree::new, src/merkle.rs:81-148 with :162-177 (call sites src/starks.rs:70-72,
  * 92-94, src/fri.rs:351). */
 int32_t ms_merkle_commit(ms_ctx* ctx, const void* d_data, uint64_t stride, uint64_t rows, uint64_t width,
