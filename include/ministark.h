@@ -266,7 +266,10 @@ int32_t ms_stark_verify(ms_ctx* ctx, const ms_stark_params* p, const void* d_con
 int32_t ms_comm_unique_id(uint8_t id128[128]);
 int32_t ms_comm_init_nccl(ms_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t world);
 int32_t ms_comm_init_local(ms_ctx* const* ctxs, int32_t world);
-int32_t ms_comm_destroy(ms_ctx* ctx); /* collective */
+/* collective: every rank of the group calls it, concurrently (local backend: on each rank's own thread -- a loop over the
+ * contexts on one thread waits for the other ranks forever).  ms_ctx_destroy alone also drops a communicator, without
+ * waiting for the peers. */
+int32_t ms_comm_destroy(ms_ctx* ctx);
 int32_t ms_comm_info(const ms_ctx* ctx, int32_t* rank, int32_t* world, const char** backend);
 /* which stages shard (default MS_SHARD_ALL); the proof does not depend on it */
 enum { MS_SHARD_TRACE_TREE = 1, MS_SHARD_COLUMNS = 2, MS_SHARD_FRI_TREES = 4, MS_SHARD_DOWNLOAD = 8, MS_SHARD_ALL = 15 };

@@ -1,7 +1,9 @@
 """The C++ host mirror (include/ministark.hpp) and its e2e example (examples/e2e_fibonacci.cpp = tests/e2e_goldilocks.rs +
 tests/e2e_babybear.rs of the reference): builds with g++ against libministark.so, its host-side half (trace, test_rng padding,
 affine form of the closures, derived parameters) equals the Python mirror's and the committed goldens, and without a GPU the
-prover half fails loudly (there is no CPU fallback).  The GPU half is tests/test_gpu_cpp_host.py."""
+prover half fails loudly (there is no CPU fallback).  examples/multi_rank_local.cpp (the multi-GPU prover driven by host threads
+through ms_comm_init_local / ms_stark_prove_multi, no Python in the process) builds and fails the same way.  The GPU half is
+tests/test_gpu_cpp_host.py."""
 import json
 import os
 import shutil
@@ -14,15 +16,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "e2e_proofs.json")
 
 
-def build_example(tmp_path) -> str:
+def build_example(tmp_path, name: str = "e2e_fibonacci") -> str:
     gxx = shutil.which("g++")
     if not gxx:
         pytest.skip("g++ not available")
     from ministark_b200 import build
 
     lib = build.build()
-    exe = str(tmp_path / "e2e_fibonacci")
-    cmd = [gxx, "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "e2e_fibonacci.cpp"),
+    exe = str(tmp_path / name)
+    cmd = [gxx, "-std=c++17", "-O2", "-pthread", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", name + ".cpp"),
            "-L" + os.path.dirname(lib), "-lministark", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -74,3 +76,13 @@ def test_cpp_prover_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, "prove", str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 3 and "no usable CUDA device" in r.stderr  # ministark::Error, not a silent CPU path
     assert not os.path.exists(tmp_path / "Goldilocks.proof")
+
+
+def test_cpp_multi_rank_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    import torch
+
+    exe = build_example(tmp_path, "multi_rank_local")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the example runs in tests/test_gpu_cpp_host.py")
+    r = subprocess.run([exe, "2", "10", "4"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3 and "no usable CUDA device" in r.stderr
