@@ -227,6 +227,18 @@ class ShardedCommitter:
         self.dist.all_gather_into_tensor(allg, mine[:n_mine].contiguous(), group=self.group)
         return self.ops.reduce(allg, self.world * n_mine, self.k)
 
+    def validate(self, n: int, w: int, cols: int, blowup: int) -> None:
+        """Every shape condition of the two hooks, checked up front: a pure function of the shape, so all ranks raise
+        together BEFORE the first collective (a rank failing alone inside a hook would leave its peers waiting in one)."""
+        if n * w % self.lpn:
+            raise ValueError("leaf count not divisible by leafs_per_node (merkle.rs:99)")
+        plan = SubtreePlan.make(n * w // self.lpn, self.k, self.world)
+        if (plan.groups_per_rank * self.lpn) % w:
+            raise ValueError("a rank's leaf groups must cover whole rows")
+        if self.lpn != cols:
+            raise ValueError("the LDE tree hashes one row per leaf group (leafs_per_node == columns)")
+        SubtreePlan.make(n * blowup, self.k, self.world)
+
     # ---- a1: the trace tree, row ranges, no bulk exchange (every rank already holds the trace)
     def trace_commit(self, trace_ptr: int, n: int, w: int) -> bytes:
         groups = n * w // self.lpn
@@ -434,6 +446,7 @@ def stark_prove_sharded(ctx, params, trace_cm, constraint_matrix: np.ndarray, ou
     if ops is None:
         ops = ctx._sharded_ops = CudaOps(ctx)
     com = ShardedCommitter(ops, int(params.trace_columns), int(params.inner_children) or 2, dist, group)
+    com.validate(n, w, w + m.shape[0], int(params.blowup_factor))
     shared = isinstance(out, SharedProofBuffer)
     buf = out.array if shared else out
     if shared and com.world > 1:

@@ -57,6 +57,23 @@ def test_subtree_plan_rejects_non_full_trees():
         SubtreePlan.make(24, 2, 4)
 
 
+def test_committer_validates_every_shape_condition_before_any_collective():
+    """the shape checks of both hooks as one pure function of the shape: all ranks raise together, before the first collective"""
+    from ministark_b200.sharded import ShardedCommitter
+
+    com = ShardedCommitter(None, 8, 2)
+    com.world = 4  # the plan arithmetic only; no process group is touched
+    com.validate(1 << 10, 4, 8, 4)
+    for n, w, cols, blowup in [(1 << 10, 3, 8, 4),      # 3072 leaves do not divide into groups of 8 (merkle.rs:99)
+                               (1 << 10, 4, 6, 4),      # leaf groups of the LDE tree != its columns
+                               (24, 4, 8, 4)]:          # 12 leaf groups over 4 ranks: 3 per rank, not a power of two
+        with pytest.raises(ValueError):
+            com.validate(n, w, cols, blowup)
+    com4 = ShardedCommitter(None, 8, 4)
+    with pytest.raises(ValueError):
+        com4.validate(1 << 10, 4, 8, 2)                 # 2^9 trace leaf groups: not a full 4-ary tree (merkle.rs:93-104)
+
+
 # ------------------------------------------------------------------------------------------ gloo
 class OracleOps:
     """Test stand-in for CudaOps: same interface, CPU tensors, compute by the oracle."""
