@@ -88,6 +88,22 @@ def test_first_match_opens_duplicate_leaves(pyref):
     assert tree.get_leaf_index(6) == 1 and tree.generate_proof(6).leaf_neighbours == [5, 6]
 
 
+def test_reference_quirk_parent_index_of_k_ary_trees_is_kept(pyref):
+    """get_parent_idx's inner-node formula (merkle.rs:205-206) is only right for binary trees: in a 4-ary tree deeper than
+    one inner level the path it walks is not the authentication path, and check_proof rejects the reference's own proof.
+    The reference never meets this (StarkConfig::new builds binary trees, its (4,4) unit test has one inner level); the
+    mirror keeps it, like every quirk of SURVEY.md App. B -- it must answer what the reference answers."""
+    leafs = list(range(1000, 1000 + 1024))
+    tree, o = _host_tree(pyref, Goldilocks, leafs, FOUR)
+    assert tree.get_parent_idx(1024 + 194) == 1255 != 1024 + 256 + 194 // 4
+    proof, ref = tree.generate_proof(leafs[777]), o.generate_proof(leafs[777])
+    assert proof.path == [list(l) for l in ref.path]
+    assert not MerkleRoot(tree.root()).check_proof(proof) and not pyref.check_proof(pyref.Goldilocks, o.root(), ref)
+    # the same leaves under a binary inner tree: the round trip holds
+    tree, _ = _host_tree(pyref, Goldilocks, leafs, TWO_FOUR)
+    assert MerkleRoot(tree.root()).check_proof(tree.generate_proof(leafs[777]))
+
+
 def test_extension_leaves(pyref):
     D = BabyBear.ext_degree
     leafs = [tuple((7 * i + d) % BabyBear.p for d in range(D)) for i in range(8)]
@@ -140,8 +156,13 @@ def test_gpu_tree_of_extension_leaves_and_edge_values(pyref, field):
     edge = [0, 1, 9, 10, 99, 100, 10**9 - 1, 10**9, F.p - 1, F.p - 2]
     base = edge + [int(x) % F.p for x in rng.integers(0, 2**62, size=1024 - len(edge))]
     tree = MerkleTree.new(F, base, MerkleTreeConfig(4, 4))
-    assert tree.nodes == list(pyref.MerkleTree(RF, base, 4, 4).nodes)
-    assert MerkleRoot(tree.root()).check_proof(tree.generate_proof(base[777]))
+    o = pyref.MerkleTree(RF, base, 4, 4)
+    assert tree.nodes == list(o.nodes)
+    assert tree.generate_proof(base[777]).path == [list(l) for l in o.generate_proof(base[777]).path]  # (quirk below included)
+    tree = MerkleTree.new(F, base, MerkleTreeConfig(4, 2))
+    assert tree.nodes == list(pyref.MerkleTree(RF, base, 4, 2).nodes)
+    proof = tree.generate_proof(base[777])
+    assert len(proof.path) == 8 and MerkleRoot(tree.root()).check_proof(proof)
     ext = [tuple(base[(D * i + d) % 1024] for d in range(D)) for i in range(256)]
     tree = MerkleTree.new(F, ext, TWO)          # the shape of a FRI round tree (starks.rs:290-295)
     o = pyref.MerkleTree(RF, ext, 2, 2)
