@@ -145,6 +145,13 @@ def workload_name(args):
             f"(BASELINE headline shape; coefficients -> evaluations on shift*<w_L>)")
 
 
+def bench_config(args):
+    """the `config` object of the JSON line: the workload and the cache statement, identical in both arms (what differs per
+    arm -- how the columns are spread over ranks, which sample of them the CPU arm times -- is in the top-level `arm` key)"""
+    return {"workload": workload_name(args),
+            "l2": "inputs (N*C*8) + outputs (L*C*8) exceed the 126 MB L2; no flush between iterations"}
+
+
 def synth_coeffs(field, n, cols, seed):
     """poly-major [cols, n] canonical coefficients (the NTT sweep treats all C columns as coefficient vectors)"""
     from ministark_b200.synth import synth_trace
@@ -210,7 +217,7 @@ def run_reference(args):
         "impl": "reference", "metric": "lde_melem_per_s", "value": val, "unit": "Melem/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": f"{cols} of {args.cols} columns per step"},
+        "config": bench_config(args), "arm": {"sample": f"{cols} of {args.cols} columns per step, {threads} host threads"},
         "cpu_baseline": {"value": val, "unit": "Melem/s", "cores": min(threads, cols), "kind": "port",
                          "sample": f"{cols} columns x 2^{args.log_rows} -> 2^{args.log_rows + int(np.log2(B))} per step, oracle port "
                                    "(reference is Rust; no toolchain in the image)"},
@@ -567,9 +574,8 @@ def run_ours(args):
             "metric": "lde_melem_per_s", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args),
-                       "l2": "inputs (N*C*8) + outputs (L*C*8) exceed the 126 MB L2; no flush between iterations",
-                       "parallelism": f"columns sharded over {world} rank(s): {[b_ - a_ for a_, b_ in column_ranges(C, world)]} columns each, no data-path collective"},
+            "config": bench_config(args),
+            "arm": {"parallelism": f"columns sharded over {world} rank(s): {[b_ - a_ for a_, b_ in column_ranges(C, world)]} columns each, no data-path collective"},
             "prove_ms": prove["prove_ms"] if prove else None,
             "roofline": {"bound": "hbm", "limiter": "int32-issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": float(ncu["dram_bytes_per_call"]) if ncu else None,

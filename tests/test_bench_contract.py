@@ -81,6 +81,10 @@ def test_reference_arm_prints_a_valid_line_without_a_gpu():
     assert d["e2e"] == {"value": d["value"], "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["prove"]["proof_bytes"] > 0 and d["prove_ms"] > 0
+    # both arms describe the workload with the same `config` object (the driver compares them); what differs per arm is in `arm`
+    assert set(d["config"]) == {"workload", "l2"} and "sample" in d["arm"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": bench_config(args)') == 2
     # ranks other than 0 of a torchrun launch exit without work or output
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
