@@ -220,6 +220,7 @@ int stark_verify(Ctx* c, const ms_stark_params& p, const typename F::T* d_constr
                 if (strict && i > 0 && !path_ok) return reject(237);
             }
             const uint64_t nq = rd.u64();
+            if (rd.bad || nq > (rd.len - rd.pos) / sizeof(E)) return reject(-2);  // a tampered count: nq * sizeof(E) must not wrap
             const uint8_t* qraw = rd.take(nq * sizeof(E));
             if (rd.bad) return reject(-2);
             uint64_t qlen = nq;  // trailing zero coefficients do not count (DensePolynomial)
