@@ -374,7 +374,7 @@ struct StarkProof {
         MINISTARK_ASSERT(raw.size() >= 24 + 64 && std::memcmp(raw.data(), "MSTARKP1", 8) == 0, "not a proof dump");
         u64 alen;
         std::memcpy(&alen, raw.data() + 16, 8);
-        MINISTARK_ASSERT(raw.size() >= 24 + alen + 64, "truncated proof dump");
+        MINISTARK_ASSERT(alen <= raw.size() - 24 - 64, "truncated proof dump");  // (not 24 + alen + 64: a tampered length must not wrap)
         p.arthur.assign(raw.begin() + 24, raw.begin() + 24 + (size_t)alen);
         std::memcpy(p.trace_commit, raw.data() + 24 + alen, 32);
         std::memcpy(p.constrain_trace_commit, raw.data() + 24 + alen + 32, 32);

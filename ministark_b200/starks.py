@@ -60,6 +60,7 @@ class StarkProof:  # starks.rs:21-28
         arthur = take(rd64())
         tc, cc = take(32), take(32)
         Q, Cn = rd64(), rd64()
+        assert Q * Cn * D * bs <= len(raw) - pos and (Cn > 0 or Q == 0)  # tampered counts: no allocation beyond the dump
         cq = [[ext() for _ in range(Cn)] for _ in range(Q)]
         vq = [ext() for _ in range(rd64())]
         points, queries, quotients = [], [], []

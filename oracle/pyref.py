@@ -1160,6 +1160,7 @@ def deserialize_proof(raw: bytes) -> Tuple[StarkField, StarkProof]:
     arthur = take(rd64())
     tc, cc = take(32), take(32)
     Q, Cn = rd64(), rd64()
+    assert Cn > 0 or Q == 0  # (a tampered count must not make this loop without consuming bytes)
     cq = [[ext() for _ in range(Cn)] for _ in range(Q)]
     vq = [ext() for _ in range(rd64())]
     points, queries, quotients = [], [], []

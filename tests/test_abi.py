@@ -143,6 +143,22 @@ def test_proof_dump_parser_round_trips_the_oracle_proofs(name, steps, pyref):
     for gr, rr in zip(got.fri_proof.quotients, ref.fri_proof.quotients):
         for gq, rq in zip(gr, rr):
             assert [norm(e) for e in gq] == [norm(e) for e in rq]
+    # tampered counts end in an AssertionError (or parse, where the word was data), never in an unbounded loop or allocation:
+    # every u64 of the first kilobyte after the commitments blown up, and the (Q, C) pair of the openings as (2^60, 0)
+    import struct
+
+    at = 24 + len(ref.arthur) + 64
+    for off in range(at, min(at + 1024, len(raw) - 8), 8):
+        bad = bytearray(raw)
+        bad[off:off + 8] = struct.pack("<Q", (1 << 60) + 1)
+        try:
+            StarkProof.from_bytes(bytes(bad))  # the word was data, not a count
+        except AssertionError:
+            pass
+    bad = bytearray(raw)
+    bad[at:at + 16] = struct.pack("<QQ", 1 << 60, 0)
+    with pytest.raises(AssertionError):
+        StarkProof.from_bytes(bytes(bad))
 
 
 def test_rust_shim_binds_every_declared_symbol():
