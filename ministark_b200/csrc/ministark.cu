@@ -362,6 +362,7 @@ int32_t ms_fri_query(ms_ctx* c, const void* d_prev_poly, uint64_t poly_stride, u
 
 int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* rounds, uint64_t* cq, uint64_t* fq) {
     ms::StarkDerived d;
+    if (!p || (field != MS_FIELD_GOLDILOCKS && field != MS_FIELD_BABYBEAR)) return MS_ERR_BAD_SHAPE;
     int rc = ms::stark_derive(field, *p, &d);
     if (rc != MS_OK) return rc;
     if (rounds) *rounds = d.rounds;
@@ -372,6 +373,7 @@ int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* round
 
 uint64_t ms_stark_proof_bound(int32_t field, const ms_stark_params* p, uint64_t n, uint64_t cols) {
     ms::StarkDerived d;
+    if (!p || (field != MS_FIELD_GOLDILOCKS && field != MS_FIELD_BABYBEAR)) return 0;
     if (ms::stark_derive(field, *p, &d) != MS_OK) return 0;
     return field == MS_FIELD_GOLDILOCKS ? ms::proof_size_bound<ms::GL>(*p, d, n, cols) : ms::proof_size_bound<ms::BB>(*p, d, n, cols);
 }

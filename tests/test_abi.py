@@ -196,3 +196,42 @@ def test_product_does_not_touch_the_oracle():
                 code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("#", "//", "*", '"""')))
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", code, flags=re.M), f
                 assert "liboracle" not in code, f
+
+
+def test_context_free_entry_points_survive_edge_values():
+    """ms_merkle_node_count, ms_stark_derive, ms_stark_proof_bound, ms_shard_plan take no context and run anywhere: zeros, ones,
+    non powers of two, 2^32, 2^63, 2^64 - 1, bad field ids and negative ranks come back as a value or an error code (no
+    division by zero, no endless loop)."""
+    import ctypes as C
+    import faulthandler
+
+    from ministark_b200 import _lib
+    from ministark_b200._lib import StarkParams
+
+    faulthandler.enable()
+    lib = _lib.load()
+    vals = [0, 1, 2, 3, 4, 7, 8, 16, 20, 63, 64, 100, 1 << 20, (1 << 32) - 1, 1 << 32, 1 << 63, (1 << 64) - 1]
+    for n in vals:
+        for k in vals:
+            lib.ms_merkle_node_count(n, k)
+    # digests for the leaf-group counts of merkle.rs:399-419 (16 leaves under TWO / TWO_FOUR / FOUR / SIXTEEN); 12 groups 4-ary: not full
+    assert [lib.ms_merkle_node_count(g, k) for g, k in ((8, 2), (4, 2), (4, 4), (1, 16), (12, 4))] == [15, 7, 5, 1, 0]
+    r, cq, fq = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    for f in (0, 1, 2, -1):
+        for sec in vals:
+            for b in vals:
+                for steps in vals:
+                    p = StarkParams(sec, b, steps, 8, 2)
+                    rc = lib.ms_stark_derive(f, C.byref(p), C.byref(r), C.byref(cq), C.byref(fq))
+                    assert rc != 0 or (f in (0, 1) and sec >= 20)
+                    for n in (0, 1, 16, 1 << 22, 1 << 63, (1 << 64) - 1):
+                        lib.ms_stark_proof_bound(f, C.byref(p), n, 32)
+    a, b_, per, left = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    for cols in vals:
+        for groups in vals:
+            for k in (0, 1, 2, 3, 4, 1 << 63):
+                for world in (-1, 0, 1, 2, 3, 8, 64, 1 << 20):
+                    for rank in (-1, 0, 1, 7):
+                        rc = lib.ms_shard_plan(cols, groups, k, world, rank, C.byref(a), C.byref(b_), C.byref(per), C.byref(left))
+                        if rc == 0:
+                            assert 0 <= rank < world and a.value <= b_.value <= cols
