@@ -69,6 +69,15 @@ def test_c_and_python_restatements_agree_on_random_airs(pyref, oracle, air):
     assert got == want, (air, None if got is None else len(got), None if want is None else len(want))
     if got is None:
         return
+    # the PRODUCT's proof-size bound (context-free, runs here) covers the real proof and is not wasteful (it counts every
+    # quotient with its round's padded length; the real ones are two coefficients shorter)
+    import ctypes as C
+
+    from ministark_b200 import _lib
+    from ministark_b200._lib import StarkParams
+
+    bound = int(_lib.load().ms_stark_proof_bound(field, C.byref(StarkParams(sec, blowup, n - 1, lpn, 2)), n, w + t))
+    assert len(got) <= bound <= 2 * len(got) + 4096, (air, bound, len(got))
     cons = oracle.derive_constrains(field, tr, mat, constants=cst)
     assert oracle.stark_verify(field, sec, blowup, n - 1, lpn, cons, got, strict=True) == (True, 0)
     _, parsed = R.deserialize_proof(got)
