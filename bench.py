@@ -564,12 +564,13 @@ def run_ours(args):
         alu_peak = N_SM * INT32_LANES_PER_SM * f_hz * 1e6
         alu = {"peak_thread_inst_per_s": alu_peak or None, "peak_source": f"{N_SM} SM x {INT32_LANES_PER_SM} INT32 lanes x {f_hz:.0f} MHz (median SM clock during the run)",
                "achieved_thread_inst_per_s": None, "frac": None,
-               "note": "the LDE kernels are integer-issue bound (DESIGN.md 3.1): this is the fraction that says how close they run to their own ceiling; "
-                       "both INT pipes together could issue 2x this, register-operand bandwidth permitting"}
+               "note": "the LDE kernels are integer-issue bound (DESIGN.md 3.1): frac = against the rate this instruction mix was measured to top "
+                       "out at (IMAD.WIDE and carry chains hold the dispatch port: 64 lanes/clk/SM, profiles/r02_f_ntt_math_ubench.txt); issue_frac = "
+                       "against the 128 lanes/clk/SM that plain IADD3 / LOP3 / SHF / IMAD reach (profiles/r01_d_pipes.txt, r02_i_fp64_mix.txt)"}
         if ncu and alu_peak:
             inst = float(ncu["thread_inst_executed_per_call"])
             alu.update(achieved_thread_inst_per_s=inst / (ms_step * 1e-3), frac=inst / (ms_step * 1e-3) / alu_peak,
-                       inst_source=ncu.get("source"), thread_inst_per_call=inst, thread_inst_per_element=inst / (L * C))
+                       issue_frac=inst / (ms_step * 1e-3) / (2.0 * alu_peak), inst_source=ncu.get("source"), thread_inst_per_call=inst, thread_inst_per_element=inst / (L * C))
         line = {
             "metric": "lde_melem_per_s", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
