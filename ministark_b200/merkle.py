@@ -85,11 +85,16 @@ class MerkleTree:
         assert k ** (levels - 1) == leaf_num // lpn, f"Tree is not full! input length must be a power of {k}"  # merkle.rs:100-104
         leafs = [int(x) if isinstance(x, (int, np.integer)) else tuple(int(c) for c in x) for x in inputs]
         deg = 1 if isinstance(leafs[0], int) else len(leafs[0])
+        own = ctx is None
         ctx = ctx or Context(field.field_id)
-        planes = np.array([[x] if deg == 1 else list(x) for x in leafs], dtype=object).T  # [deg, leaf_num]
-        cm = ctx.to_device(np.ascontiguousarray(planes.astype(ctx.np_dtype)))
-        _root, dev_nodes = ctx.merkle_commit(cm, lpn, k, deg=deg, want_nodes=True)
-        nodes = [bytes(row) for row in Context.nodes_to_bytes(dev_nodes)]
+        try:
+            planes = np.array([[x] if deg == 1 else list(x) for x in leafs], dtype=object).T  # [deg, leaf_num]
+            cm = ctx.to_device(np.ascontiguousarray(planes.astype(ctx.np_dtype)))
+            _root, dev_nodes = ctx.merkle_commit(cm, lpn, k, deg=deg, want_nodes=True)
+            nodes = [bytes(row) for row in Context.nodes_to_bytes(dev_nodes)]  # (a device -> host copy: synchronises)
+        finally:
+            if own:
+                ctx.close()
         assert len(nodes) == (1 - k ** levels) // (1 - k) and nodes[-1] == _root  # merkle.rs:116-118
         return cls(leafs, nodes, config, levels)
 
