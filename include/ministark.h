@@ -184,7 +184,9 @@ typedef struct ms_stark_params {
     uint64_t inner_children; /* 2 in the reference (src/starks.rs:299); 4 / 8 = BASELINE configs 3, 5 */
 } ms_stark_params;
 
-/* Parameters StarkConfig::new derives (src/starks.rs:274-277, 312-332). */
+/* Parameters StarkConfig::new derives (src/starks.rs:274-277, 312-332).  Needs no context (runs without a GPU).  MS_ERR_BAD_SHAPE: fewer
+ * than 20 security bits (the reference's assert, src/starks.rs:317-320), steps = 0, a blowup that is not a power of two >= 2, an unknown
+ * field id.  ms_stark_proof_bound returns 0 in the same cases. */
 int32_t ms_stark_derive(int32_t field, const ms_stark_params* p, uint64_t* rounds, uint64_t* constrain_queries,
                         uint64_t* fri_queries);
 
