@@ -81,6 +81,15 @@ def test_c_and_python_restatements_agree_on_random_airs(pyref, oracle, air):
     cons = oracle.derive_constrains(field, tr, mat, constants=cst)
     assert oracle.stark_verify(field, sec, blowup, n - 1, lpn, cons, got, strict=True) == (True, 0)
     _, parsed = R.deserialize_proof(got)
+    # the host mirror's parser of the dump (ministark_b200/starks.py) reads the same proof
+    from ministark_b200.starks import StarkProof
+
+    mine = StarkProof.from_bytes(got)
+    tup = lambda e: tuple(int(v) for v in (e if isinstance(e, (tuple, list)) else (e,)))
+    assert mine.arthur == bytes(parsed.arthur) and mine.trace_commit == parsed.trace_commit
+    assert [[tup(e) for e in row] for row in mine.constrain_queries] == [[tup(e) for e in row] for row in parsed.constrain_queries]
+    assert [[[tup(e) for e in q] for q in rnd] for rnd in mine.fri_proof.quotients] == [[[tup(e) for e in q] for q in rnd] for rnd in parsed.fri_proof.quotients]
+    assert [[[p.path for p in pair] for pair in rnd] for rnd in mine.fri_proof.queries] == [[[[list(l) for l in p.path] for p in pair] for pair in rnd] for rnd in parsed.fri_proof.queries]
     assert R.Stark(cfg).verify(air_obj.trace().derive_constrains(), parsed, strict=True)
     # tampered dumps: the two verifiers give the same verdict.  (Not always "rejected": the reference's verifier only uses the
     # DEGREE of a quotient polynomial, fri.rs:223-225, and cannot check round 0's paths, whose root is not in the transcript,
@@ -147,3 +156,47 @@ def test_verifiers_reject_length_fields_that_wrap(pyref, oracle, field):
         hits += 1
         pos += 8
     assert hits > 10
+
+
+@settings(max_examples=40, deadline=None, derandomize=True)
+@given(st.sampled_from([0, 1]), st.integers(1, 5), st.integers(1, 4), st.integers(0, 2**32 - 1), st.booleans())
+def test_affine_form_recovers_random_closures(field, w, t, seed, with_consts):
+    """The host mirror's probe of the AIR closures (ministark_b200/air.py TraceTable.affine_form, what crosses the C ABI instead
+    of the closures of src/air.rs:61): closures built from a random T x W matrix and constants with the DensePolynomial
+    operators come back as exactly that matrix and those constants; a closure that multiplies two trace polynomials, or a trace
+    polynomial by a non-constant one, is refused (the reference would panic at src/starks.rs:119)."""
+    from ministark_b200.air import DensePolynomial, TraceTable
+    from ministark_b200.field import FIELDS
+
+    F = FIELDS[field]
+    rng = np.random.default_rng(seed)
+    M = [[int(x) % F.p for x in rng.integers(0, 2**63, size=w)] for _ in range(t)]
+    for row in M:
+        for j in range(w):
+            if rng.random() < 0.3:
+                row[j] = 0
+    c = [int(x) % F.p if with_consts and rng.random() < 0.7 else 0 for x in rng.integers(0, 2**63, size=t)]
+    table = TraceTable(F, 7, w)
+
+    def closure(row, cst):
+        def f(P):
+            acc = DensePolynomial(F, [cst] if cst else [])
+            for j, m in enumerate(row):
+                if m:
+                    acc = acc + P[j].clone() * DensePolynomial(F, [m])
+            return acc
+        return f
+
+    for row, cst in zip(M, c):
+        table.add_transition_constrain(closure(row, cst))
+    got_m, got_c = table.affine_form()
+    assert [[int(v) for v in r] for r in got_m] == M and [int(v) for v in got_c] == c
+    if not any(c):
+        assert [[int(v) for v in r] for r in table.linear_matrix()] == M
+    bad = TraceTable(F, 7, w)
+    if rng.random() < 0.5 or w == 1:
+        bad.add_transition_constrain(lambda P: P[0].clone() * DensePolynomial(F, [1, 1]))  # times (1 + x)
+    else:
+        bad.add_transition_constrain(lambda P: P[0].clone() * P[1].clone())              # quadratic
+    with pytest.raises(ValueError):
+        bad.affine_form()
