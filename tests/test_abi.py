@@ -235,3 +235,25 @@ def test_context_free_entry_points_survive_edge_values():
                         rc = lib.ms_shard_plan(cols, groups, k, world, rank, C.byref(a), C.byref(b_), C.byref(per), C.byref(left))
                         if rc == 0:
                             assert 0 <= rank < world and a.value <= b_.value <= cols
+
+
+def test_chacha_known_answers_pin_the_test_rng_core():
+    """ark_std::test_rng() is rand 0.8's StdRng = ChaCha12 (SURVEY.md App. A 10).  The block function of the host mirror
+    (ministark_b200/air.py, behind `padding_value`) against published known answers: all-zero key / IV / counter, first
+    keystream block at 8, 12 and 20 rounds (draft-strombergson-chacha-test-vectors TC1; the 20-round one is also the
+    all-zero vector of RFC 7539 section 2.3.2's construction) -- and the oracle's copy gives the same blocks."""
+    import struct
+
+    from ministark_b200.air import _chacha_block
+    from oracle import pyref
+
+    want = {
+        8: "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e984ce172b9216f419f445367456d5619314a42a3da86b001387bfdb80e0cfe42",
+        12: "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be",
+        20: "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586",
+    }
+    for rounds, hexstr in want.items():
+        assert struct.pack("<16I", *_chacha_block([0] * 8, 0, rounds)).hex() == hexstr
+        assert struct.pack("<16I", *pyref._chacha_block([0] * 8, 0, rounds)).hex() == hexstr
+    # the 64-bit block counter occupies words 12-13 (rand_chacha): block 1 differs from block 0 and from a nonce change
+    assert _chacha_block([0] * 8, 1, 12) != _chacha_block([0] * 8, 0, 12)
