@@ -128,6 +128,8 @@ class StarkField:
         return ((a[0] * b[0] + nr * a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
 
     def ext_mul(self, a, b):
+        if self.ext_degree == 1:  # the base field used as its own "extension" (fri.rs:396-424 runs FRI over GoldilocksFp)
+            return ((a[0] * b[0]) % self.p,)
         if self.ext_degree == 2:  # Goldilocks: u^2 = 7 (field.rs:55)
             return self._fp2_mul(a, b, 7)
         # BabyBear: u^2 = 11 (field.rs:84).  Effective quartic tower: v^2 = u.  ark-ff 0.5.0's QuadExtField

@@ -468,3 +468,48 @@ def test_e2e_prove_verify(field, steps, pyref):
     bad.validity_queries[0] = F.ext_add(bad.validity_queries[0], F.ext_one())
     with pytest.raises(AssertionError):
         stark.verify(cons, bad)
+
+
+# ---- the reference's own FRI unit tests (src/fri.rs:396-454) ------------------------------------------
+def test_reference_fri_unit_test_over_the_base_field(pyref):
+    """fri.rs:396-424 `test_fri_prover_new`: coefficients 0..4 over GoldilocksFp (the base field as its own extension), 3 rounds,
+    3 queries, blowup 2, (2,2) trees, IO pattern new_fri("🍟", 3, 3).  The reference asserts nothing about the output; the
+    restatement must run it through, and (beyond the reference) its own verifier accepts the result."""
+    import dataclasses
+
+    R = pyref
+    F1 = dataclasses.replace(R.Goldilocks, name="GoldilocksFp", ext_degree=1)
+    poly = [(i,) for i in range(4)]
+    io = R.add_fri_iopattern(R.IOPattern("\U0001F35F"), F1, 3, 3)
+    assert io.as_bytes().startswith("\U0001F35F".encode() + b"\x00S24(DEEP) FRI: pick random z\x00A16(DEEP) FRI: degree one B polynomial")
+    merlin = R.Transcript(F1, io)
+    fri = R.Fri(F1, R.FriConfig(queries=3, blowup_factor=2, rounds=3))
+    assert fri.cfg.rounds == 3                                                        # fri.rs:421
+    proof = fri.prove(merlin, poly)
+    assert [len(r) for r in proof.points] == [3, 3] and len(merlin.transcript) == 2 * (2 * 8 + 32)
+    assert fri.verify(proof, R.Transcript(F1, io, proof=bytes(merlin.transcript)), strict=True)
+
+
+def test_reference_fri_unit_test_prove_then_verify(pyref):
+    """fri.rs:426-454 `test_fri_new`: the same polynomial over GoldilocksFp2, rounds = 3, ONE query although the IO pattern is
+    built for two (new_fri("🍟", rounds, 2), fri.rs:433-434: the query phase squeezes 8 of the 16 bytes the pattern allows),
+    then `assert!(fri.verify(proof, &mut arthur).unwrap())`."""
+    R = pyref
+    F = R.Goldilocks
+    poly = [(i, 0) for i in range(4)]                                                  # (0..4).map(GoldilocksFp2::from)
+    io = R.add_fri_iopattern(R.IOPattern("\U0001F35F"), F, 3, 2)
+    merlin = R.Transcript(F, io)
+    fri = R.Fri(F, R.FriConfig(queries=1, blowup_factor=2, rounds=3))
+    proof = fri.prove(merlin, poly)
+    transcript = bytes(merlin.transcript)
+    assert len(transcript) == 2 * (2 * 16 + 32)
+    # codeword sizes 8 -> 4 -> 2 (fri.rs:74, 374-376): quotient of the degree-3 round polynomial has 2 coefficients, the next none
+    assert [[len(q) for q in r] for r in proof.quotients] == [[2], [0]]
+    assert [[len(p.path) for p in pair] for r in proof.queries for pair in r] == [[2, 2], [1, 1]]
+    assert fri.verify(proof, R.Transcript(F, io, proof=transcript))                    # fri.rs:452-453
+    assert fri.verify(proof, R.Transcript(F, io, proof=transcript), strict=True)
+    # a wrong point is caught by the reference's own checks (fri.rs:217-219, 233)
+    (x1, y1), p2, p3 = proof.points[0][0]
+    proof.points[0][0] = [(x1, F.ext_add(y1, F.ext_one())), p2, p3]
+    with pytest.raises(AssertionError):
+        fri.verify(proof, R.Transcript(F, io, proof=transcript))
